@@ -1,0 +1,121 @@
+// Shared helpers for the sm_100a kernels of the attention-lvcsr hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace lvsr {
+
+namespace cg = cooperative_groups;
+
+extern thread_local std::string g_last_error;
+extern long long g_launch_count;
+
+int set_error(const char* fmt, ...);
+
+// Optional per-launch CUDA-event timing (see lvsr_profile_enable in include/lvsr_b200.h).
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(const char* kernel_class, cudaStream_t stream);
+  ~ProfScope();
+};
+
+#define LVSR_CUDA_OK(expr)                                                          \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return ::lvsr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                 \
+  } while (0)
+
+#define LVSR_CHECK(cond, ...)                          \
+  do {                                                 \
+    if (!(cond)) return ::lvsr::set_error(__VA_ARGS__); \
+  } while (0)
+
+#define LVSR_LAUNCH_CHECK()                                                         \
+  do {                                                                              \
+    ::lvsr::g_launch_count++;                                                       \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess)                                                          \
+      return ::lvsr::set_error("kernel launch failed: %s (%s:%d)",                  \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);         \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device math: accurate enough for the 1e-4 gate against the float64 oracle ----
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// tanh via exp: |err| ~ 1e-7 absolute, which is what energies / states need.
+__device__ __forceinline__ float tanhf_acc(float x) {
+  float ax = fabsf(x);
+  if (ax < 0.04f) {  // odd Taylor polynomial keeps RELATIVE accuracy near 0
+    float x2 = x * x;
+    return x * (1.0f + x2 * (-0.33333333f + x2 * 0.13333334f));
+  }
+  float e = __expf(-2.0f * ax);
+  float t = (1.0f - e) / (1.0f + e);
+  return copysignf(t, x);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Reduce N per-lane partial sums across the 32 lanes of a warp with a halving
+// exchange: after the call acc[0 .. max(1, N/32)) hold fully reduced values and the
+// returned base says which: acc[j] == sum over lanes of original acc[base + j].
+// When N < 32 the tail stages are plain butterflies, so lane groups hold duplicates.
+template <int NTOT, int n, int o>
+__device__ __forceinline__ void rs_stage(float (&acc)[NTOT], int lane, int& base) {
+  if constexpr (o > 0) {
+    if constexpr (n > 1) {
+      constexpr int h = n / 2;
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        float mine = up ? acc[j + h] : acc[j];
+        float theirs = up ? acc[j] : acc[j + h];
+        acc[j] = mine + __shfl_xor_sync(0xffffffffu, theirs, o);
+      }
+      if (up) base += h;
+      rs_stage<NTOT, h, o / 2>(acc, lane, base);
+    } else {
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      rs_stage<NTOT, 1, o / 2>(acc, lane, base);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ int warp_reduce_scatter(float (&acc)[N], int lane) {
+  int base = 0;
+  rs_stage<N, N, 16>(acc, lane, base);
+  return base;
+}
+
+// The index base warp_reduce_scatter<N> will return for this lane (pure function of lane).
+template <int N>
+__device__ __forceinline__ int rs_base(int lane) {
+  int base = 0, n = N;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      if (lane & o) base += n;
+    }
+  }
+  return base;
+}
+
+}  // namespace lvsr

@@ -1,0 +1,128 @@
+// Internal (C++) launch interfaces of the kernels behind the C ABI in include/lvsr_b200.h.
+#pragma once
+#include "common.cuh"
+
+namespace lvsr {
+
+// ---- gemm.cu ------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A;          // row r lives at A + (r / rows_per_block) * block_stride + (r % rows_per_block) * lda
+  int M, K;
+  int rows_per_block;
+  long long block_stride;
+  int lda;
+  const float* W;          // [K, N] row-major, leading dimension ldw
+  int N, ldw;
+  const float* bias;       // [N] or nullptr
+  float* C;                // [M, N], leading dimension ldc
+  int ldc;
+  int accumulate;          // C += ... instead of C = ...
+};
+int gemm_bias(const GemmArgs& g, cudaStream_t stream);
+
+inline GemmArgs make_gemm(const float* A, int M, int K, const float* W, int N, const float* bias,
+                          float* C, bool accumulate = false) {
+  GemmArgs g;
+  g.A = A; g.M = M; g.K = K; g.rows_per_block = M > 0 ? M : 1; g.block_stride = 0; g.lda = K;
+  g.W = W; g.N = N; g.ldw = N; g.bias = bias; g.C = C; g.ldc = N; g.accumulate = accumulate ? 1 : 0;
+  return g;
+}
+
+// ---- bigru.cu -----------------------------------------------------------------------
+struct BiGruArgs {
+  const float* pre;        // [T*B, 6D]: per direction [inputs D | update-gate D | reset-gate D], fwd then bwd
+  const float* mask;       // [T, B] view (time stride mask_tstride) or nullptr
+  long long mask_tstride;
+  const float *Wg_f, *Ws_f, *h0_f;   // forward  state_to_gates [D,2D], state_to_state [D,D], initial_state [D]
+  const float *Wg_b, *Ws_b, *h0_b;   // backward
+  float* out;              // [ceil(T/subsample), B, 2D] (forward units first)
+  int T, B, D, subsample;
+};
+bool bigru_supported(int D);
+int bigru_layer(const BiGruArgs& a, cudaStream_t stream);
+
+// ---- attention.cu -------------------------------------------------------------------
+struct PriorParams {
+  int type;                // LVSR_PRIOR_*
+  double initial_begin, initial_end, min_speed, max_speed, before, after;
+};
+
+// Window of take_glimpses (lvsr/bricks/attention.py:123-163), computed on device.
+//   win[0] = begin, win[1] = end (global cut); lohi[2r], lohi[2r+1] = per-row strict bounds
+struct WindowArgs {
+  const float* weights;    // [R, Tp] previous alignment
+  const long long* step;   // [R] (only step[0] is used, by the expanding prior); may be nullptr (= 0)
+  long long step_offset;   // added to step[0] (teacher forcing: the step index)
+  int R, Tp;
+  PriorParams prior;
+  int* win;                // [2]
+  float* lohi;             // [2R]
+};
+int attention_window(const WindowArgs& a, cudaStream_t stream);
+
+struct AttStepArgs {
+  const float* P;          // [Tp, U, M] preprocessed attended
+  const float* H;          // [Tp, U, E] attended
+  const float* maskH;      // [Tp, U]
+  const int* row_utt;      // [R] or nullptr (identity)
+  const float* q;          // [R, M]  states . W_state
+  const float* w_prev;     // [R, Tp]
+  const int* win;          // [2] from attention_window
+  const float* lohi;       // [2R]
+  const float* filt;       // [K, 2n+1]
+  const float* Wh;         // [K, M]
+  const float* v;          // [M]
+  float v_bias;            // energy bias (only when normalizer != softmax)
+  float* w_out;            // [R, Tp]
+  float* e_out;            // [R, Tp]
+  float* ctx;              // [R, E]
+  int R, U, Tp, M, E, K, n, normalizer;
+};
+int attention_step(const AttStepArgs& a, cudaStream_t stream);
+int attention_max_cluster();
+
+// ---- decoder.cu ---------------------------------------------------------------------
+// out[R,N] = epilogue( X1[R,K1].W1[K1,N] (+ X2[R,K2].W2[K2,N2], columns < N2 only) + add[arow[r]] )
+enum { DENSE_PLAIN = 0, DENSE_GATES = 1, DENSE_CAND = 2 };
+struct DenseArgs {
+  const float* X1; int K1; const float* W1;        // W1 [K1, N]
+  const float* X2; int K2; const float* W2; int N2; // W2 [K2, N2], may be null
+  const float* add;        // [*, N] addend rows or nullptr
+  const long long* arow;   // [R] row index into add (labels) or nullptr (identity)
+  int R, N, mode;
+  // DENSE_PLAIN: out[R,N]
+  float* out;
+  // DENSE_GATES (N = 3C): cols [0,C) update -> z[R,C]; [C,2C) reset -> hr[R,C] = s*r; [2C,3C) -> ai[R,C]
+  // DENSE_CAND  (N = C):  c = tanh(acc + ai); s' = c*z + s*(1-z); optional row mask blend -> out[R,C]
+  const float* s;          // [R, C] current states
+  float* z; float* hr; float* ai;
+  const float* rmask;      // [R] or nullptr
+  int C;
+};
+int dense_step(const DenseArgs& a, cudaStream_t stream);
+
+// readouts -> -log softmax.  merged [R, Cpm] (already merge + nothing else): adds bias, maxout/relu,
+// Linear(Cpm/pieces -> V), log-softmax; writes either all V costs or the cost of labels[r].
+struct ReadoutArgs {
+  const float* merged;     // [R, Cpm]
+  const float* b_pm;       // [Cpm]
+  const float* Wo;         // [Cpm/pieces, V]
+  const float* bo;         // [V]
+  int R, Cpm, pieces, V, act;   // act: LVSR_ACT_*
+  const long long* labels; // [R] or nullptr
+  const float* lmask;      // [R] or nullptr (multiplies the picked cost)
+  float* costs_all;        // [R, V] or nullptr
+  float* costs_picked;     // [R] or nullptr
+};
+int readout_costs(const ReadoutArgs& a, cudaStream_t stream);
+
+// small utility kernels
+int fill_f32(float* p, long long n, float v, cudaStream_t stream);
+int fill_i64(long long* p, long long n, long long v, cudaStream_t stream);
+int broadcast_rows(float* dst, const float* src, int R, int N, cudaStream_t stream);   // dst[r,:] = src[:]
+int onehot_rows(float* dst, int R, int N, cudaStream_t stream);                         // dst[r,:] = e_0
+int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream);
+int gather_time_subsample(float* dst, const float* src, int Tout, int k, long long row_elems,
+                          cudaStream_t stream);                                         // dst[t] = src[t*k]
+
+}  // namespace lvsr

@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the attention-lvcsr hot path (encoder + teacher-forced
+attention decoder) at the BASELINE.json metric configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic batch per GPU:
+B=64 utterances x T=1000 frames x F=40 filterbanks, 4x pyramidal BiGRU(256)
+(subsample [1,1,2,2] -> T'=250), content+location attention (M=512, K=10, n=100),
+GRU(256) decoder, L=125 teacher-forced steps, Maxout(2) readout over V=32 symbols.
+Multi-GPU: utterance batches shard across ranks (weak scaling, no data-path collective).
+
+Prints ONE JSON line on rank 0 (see the task contract): `value` = frames/s with inputs
+resident in HBM; `e2e` = same metric through the host-buffer C-ABI call
+(lvsr_recognizer_cost_host: pinned host inputs, H2D + D2H inside the timed region);
+`roofline` = attention-step kernel, algorithmic bytes / CUDA-event time vs the measured
+HBM peak; `cpu_baseline` = float32 twin of the oracle on a bounded sample of the workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(B=64, T=1000, F=40, L=125, V=32)
+NET = dict(num_features=40, dims_bidir=[256, 256, 256, 256], subsample=[1, 1, 2, 2], dim_dec=256,
+           dim_matcher=512, conv_n=100, conv_num_filters=10, num_phonemes=32, post_merge_dims=[256],
+           maxout_pieces=2)
+METRIC = "encoder+decoder frames/sec at batch64x1000frx40fb"
+
+
+def synthetic_batch(B, T, F, L, V, seed):
+    """Synthetic utterances of the BASELINE shape: lengths U{0.6T..T} (max == T), N(0,1)
+    features, right-padded 0/1 masks, labels U{0..V-2} + eos of length ~T_b/8 (max == L)."""
+    rng = np.random.RandomState(seed)
+    lens = rng.randint(int(math.ceil(0.6 * T)), T + 1, size=B)
+    lens[rng.randint(B)] = T
+    x = rng.normal(size=(T, B, F)).astype(np.float32)
+    m = (np.arange(T)[:, None] < lens[None, :]).astype(np.float32)
+    x *= m[:, :, None]
+    lab_lens = np.minimum(L, np.ceil(lens / 8.0).astype(int))
+    lab_lens[lens == T] = L
+    labels = np.zeros((L, B), dtype=np.int64)
+    lm = np.zeros((L, B), dtype=np.float32)
+    for b in range(B):
+        n = int(lab_lens[b])
+        labels[:n - 1, b] = rng.randint(0, V - 1, size=n - 1)
+        labels[n - 1, b] = V - 1
+        lm[:n, b] = 1
+    return x, m, labels, lm
+
+
+def init_values(shapes, seed=1, scale=10.0):
+    """Random-init weights of the architecture (WSJ scheme x10 'trained-like')."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name, shape in shapes.items():
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "b":
+            v = np.zeros(shape)
+        elif leaf in ("state_to_state", "state_to_gates"):
+            d = shape[0]
+            blocks = []
+            for _ in range(shape[1] // d):
+                q, r = np.linalg.qr(rng.randn(d, d))
+                blocks.append(q * np.sign(np.diag(r)))
+            v = np.hstack(blocks)
+        elif leaf == "initial_state":
+            v = rng.normal(0, 0.001, size=shape) * scale
+        else:
+            v = rng.normal(0, 0.01, size=shape) * scale
+        out[name] = v.astype(np.float32)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def attention_step_bytes(B, Tw, M, E):
+    """ALGORITHMIC bytes of one attention+decoder step: read P_cut and H_cut
+    once, read alpha_prev + mask, write alpha + energies."""
+    return 4 * Tw * B * (M + E) + 4 * B * Tw * 4
+
+
+def cpu_reference_run(steps, warmup, sample_B=16):
+    """The reference's CPU path cannot run here (Python-2 Theano): time its
+    restatement (oracle, float32 twin, numpy+BLAS on all host cores) on a bounded sample of
+    the SAME workload: `sample_B` utterances of T=1000 frames, L=125 teacher-forced steps."""
+    from oracle import lvsr_oracle as O
+    W = WORKLOAD
+    cfg = O.make_config(**NET)
+    params = O.cast_params(O.init_params(cfg, seed=1, scale=10.0), np.float32)
+    x, m, labels, lm = synthetic_batch(sample_B, W["T"], W["F"], W["L"], W["V"], seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.recognizer_cost(cfg, params, x, m, labels, lm)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    fps = sample_B * W["T"] / float(np.mean(times))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count()
+    return fps, float(np.mean(times)) * 1e3, dict(
+        value=fps, unit="frames/s", cores=cores, kind="port",
+        sample="%d utterances x %d frames x %d fbank, %d decoder steps, float32 numpy+BLAS restatement of the "
+               "Theano CPU path (Theano itself cannot run: SURVEY.md 8c)" % (sample_B, W["T"], W["F"], W["L"]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = WORKLOAD
+    config = {"workload": "configs[metric]: WSJ-shaped synthetic, batch %d x %d frames x %d fbank per GPU, "
+                          "4-layer pyramidal BiGRU(256) + content+location attention + GRU(256) decoder, "
+                          "%d teacher-forced steps" % (W["B"], W["T"], W["F"], W["L"]),
+              "global_batch": W["B"] * world, "frames": W["T"], "parallelism": "dp%d (utterance shards)" % world,
+              "l2": "L2 flushed (256 MiB write) between timed iterations"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 3))
+        fps, ms, cb = cpu_reference_run(steps, min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": cb,
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    assert torch.cuda.is_available(), "bench.py needs a GPU"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    rec = pkg.SpeechRecognizer(
+        input_dims={"recordings": W["F"]}, input_num_chars={}, eos_label=W["V"] - 1, num_phonemes=W["V"],
+        dim_dec=NET["dim_dec"], dims_bidir=NET["dims_bidir"], subsample=NET["subsample"], conv_n=NET["conv_n"],
+        conv_num_filters=NET["conv_num_filters"], dim_matcher=NET["dim_matcher"],
+        post_merge_dims=NET["post_merge_dims"], post_merge_activation=pkg.Maxout(2),
+        enc_transition=pkg.GatedRecurrent, dec_transition=pkg.GatedRecurrent, device=dev)
+    rec.set_parameter_values(init_values(rec.parameter_shapes()))
+    lib = pkg._lib.load()
+
+    x, m, labels, lm = synthetic_batch(W["B"], W["T"], W["F"], W["L"], W["V"], seed=1234 + rank)
+    xd, md = torch.as_tensor(x, device=dev), torch.as_tensor(m, device=dev)
+    yd, ymd = torch.as_tensor(labels, device=dev), torch.as_tensor(lm, device=dev)
+    xh, mh = torch.as_tensor(x).pin_memory(), torch.as_tensor(m).pin_memory()
+    yh, ymh = torch.as_tensor(labels).pin_memory(), torch.as_tensor(lm).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        att, attm = rec.encode(xd, md)
+        return rec.cost_matrix(yd, ymd, att, attm)
+
+    def step_host():
+        return rec.cost(xh.numpy(), mh.numpy(), yh.numpy(), ymh.numpy())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                       # evict L2 between timed iterations
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            total_ms += a.elapsed_time(b)
+        return total_ms
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    step_host()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.lvsr_launch_count(1)
+    barrier()
+    ms_dev = timed(step_device, args.steps)
+    barrier()
+    launches = int(lib.lvsr_launch_count(1))
+    ms_dev = max_over_ranks(ms_dev)
+
+    # end to end through the host-buffer C-ABI call (wall clock around a synchronising call)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize(dev)
+    ms_host = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # per-kernel-class device time (second pass with CUDA events around every launch)
+    prof = {}
+    lib.lvsr_profile_enable(1)
+    step_device()
+    torch.cuda.synchronize(dev)
+    import ctypes as C
+    for cls in ("gemm", "bigru", "attention", "window", "dense", "readout"):
+        tot, cnt = C.c_double(), C.c_int64()
+        lib.lvsr_profile_read(cls.encode(), C.byref(tot), C.byref(cnt))
+        prof[cls] = {"ms": tot.value, "launches": cnt.value}
+    lib.lvsr_profile_enable(0)
+
+    if rank != 0:
+        return 0
+
+    frames = W["B"] * W["T"] * world
+    ms_step = ms_dev / args.steps
+    value = frames / (ms_step * 1e-3)
+    e2e_value = frames / (ms_host / args.steps * 1e-3)
+    peaks, peak_src = measured_peaks()
+    Tp = rec.encoded_length(W["T"])
+    att = prof["attention"]
+    step_bytes = attention_step_bytes(W["B"], Tp, NET["dim_matcher"], 2 * NET["dims_bidir"][-1])
+    att_us = att["ms"] * 1e3 / max(1, att["launches"])
+    achieved = step_bytes / (att_us * 1e-6) / 1e9 if att_us > 0 else 0.0
+    # the whole decoder step (attention + window + dense GRU pieces), the north-star's unit
+    dec_ms = prof["attention"]["ms"] + prof["window"]["ms"] + prof["dense"]["ms"]
+    dec_us = dec_ms * 1e3 / max(1, att["launches"])
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_value, "unit": "frames/s",
+                "h2d_bytes_per_step": int(x.nbytes + m.nbytes + labels.nbytes + lm.nbytes),
+                "d2h_bytes_per_step": int(W["L"] * W["B"] * 4)},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "att_step_kernel (attention step of the decoder)",
+                     "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": step_bytes, "us_per_launch": att_us,
+                     "decoder_step_us": dec_us,
+                     "decoder_step_frac": (step_bytes / (dec_us * 1e-6) / 1e9 / peaks["hbm_gbs"]) if dec_us > 0 else 0.0,
+                     "how": "CUDA events around every launch of the class in a separate profiled pass"},
+        "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "kernel_launches_per_step": {k: v["launches"] for k, v in prof.items()},
+    }
+    if not args.no_cpu_baseline:
+        _, _, cb = cpu_reference_run(1, 0)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

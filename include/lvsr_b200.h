@@ -1,0 +1,145 @@
+/*
+ * lvsr_b200.h -- C ABI of the B200-native attention-lvcsr hot path.
+ *
+ * The reference (rizar/attention-lvcsr) has no FFI of its own on this path: Theano
+ * generates and compiles C at run time and the "operator ABI" is the set of compiled
+ * theano.function objects that Blocks/lvsr call.  Each entry point below replaces one
+ * of those compiled functions 1:1 (tier b3); the reference-side
+ * binding a maintainer would add is a ctypes stub, shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers, sizes.  No torch / C++ types.
+ *   - all tensors are TIME-MAJOR and contiguous, float32 unless noted, exactly the
+ *     layouts the reference feeds its compiled functions
+ *     (lvsr/datasets/__init__.py:22-29,308; lvsr/bricks/recognizer.py:129-133,353-361).
+ *   - `*_dev` pointers are device pointers on the model's GPU, `*_host` are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     stream-ordered and never synchronise, except the `*_host` convenience calls,
+ *     which copy H2D, compute, copy D2H and synchronise the stream before returning.
+ *   - every call returns 0 on success, non-zero on error; lvsr_last_error() then
+ *     describes the failure (thread-local).
+ *   - one model handle per GPU; a handle is not thread-safe.
+ */
+#ifndef LVSR_B200_H
+#define LVSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lvsr_model lvsr_model;
+
+enum { LVSR_MAX_LAYERS = 8 };
+enum { LVSR_NORM_SOFTMAX = 0, LVSR_NORM_LOGISTIC = 1, LVSR_NORM_RELU = 2 };
+enum { LVSR_ACT_MAXOUT = 0, LVSR_ACT_RELU = 1, LVSR_ACT_TANH = 2, LVSR_ACT_IDENTITY = 3 };
+enum { LVSR_PRIOR_EXPANDING = 0, LVSR_PRIOR_WINDOW_MEAN = 1, LVSR_PRIOR_WINDOW_MEDIAN = 2 };
+
+/* The subset of config['net'] the path depends on
+ * (SpeechRecognizer.__init__, lvsr/bricks/recognizer.py:176-204). */
+typedef struct {
+  int32_t num_features;            /* F: input_dims['recordings']                     */
+  int32_t num_layers;              /* len(dims_bidir)                                  */
+  int32_t dims_bidir[LVSR_MAX_LAYERS];
+  int32_t subsample[LVSR_MAX_LAYERS];
+  int32_t dim_dec;                 /* C                                                */
+  int32_t dim_matcher;             /* M (defaults to dim_dec, recognizer.py:225-226)   */
+  int32_t conv_n;                  /* n, filter length 2n+1                            */
+  int32_t conv_num_filters;        /* K                                                */
+  int32_t num_phonemes;            /* V; the lookup table has V+1 rows                 */
+  int32_t dim_feedback;            /* Cfb (dim_dec unless dim_output_embedding)        */
+  int32_t post_merge_dim;          /* post_merge_dims[0]                               */
+  int32_t maxout_pieces;           /* num_pieces of Maxout, 1 otherwise                */
+  int32_t post_merge_activation;   /* LVSR_ACT_* (reference default: Tanh)             */
+  int32_t use_states_for_readout;
+  int32_t energy_normalizer;       /* LVSR_NORM_*                                      */
+  int32_t prior_type;              /* LVSR_PRIOR_*                                     */
+  double prior_initial_begin, prior_initial_end, prior_min_speed, prior_max_speed;
+  double prior_before, prior_after;
+} lvsr_config;
+
+const char* lvsr_last_error(void);
+int lvsr_version(void);
+
+/* ---- model life cycle ----------------------------------------------------------- */
+/* SpeechRecognizer(**config['net']) + allocate(): lvsr/main.py:213-221. Uses the
+ * CUDA device current on the calling thread. */
+int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out);
+int lvsr_model_destroy(lvsr_model* m);
+
+/* Parameter table in Blocks order/names ("/recognizer/encoder/bidir0/forward/fork/fork_inputs.W"
+ * ...): Selector.get_parameters, libs/blocks/blocks/select.py:160-220. */
+int lvsr_model_num_params(const lvsr_model* m);
+const char* lvsr_model_param_name(const lvsr_model* m, int index);
+int lvsr_model_param_shape(const lvsr_model* m, int index, int64_t shape[2], int32_t* ndim);
+/* Model.set_parameter_values / get_parameter_values (lvsr/bricks/recognizer.py:408-412). */
+int lvsr_model_set_param(lvsr_model* m, const char* name, const float* values_host, int64_t count);
+int lvsr_model_get_param(const lvsr_model* m, const char* name, float* values_host, int64_t count);
+/* Re-derive the packed kernel-side weights after parameters changed. */
+int lvsr_model_finalize(lvsr_model* m);
+
+/* ---- encoder: BeamSearch.context_computer / Encoder.apply -------------------------
+ * (libs/blocks/blocks/search.py:97-99; lvsr/bricks/__init__.py:71-78).
+ * recordings [T,B,F], mask [T,B] (NULL = no mask) -> attended [T',B,E], attended_mask [T',B]
+ * with T' = lvsr_encoded_length(T), E = 2*dims_bidir[last]. */
+int lvsr_encoded_length(const lvsr_model* m, int32_t T);
+int lvsr_encoded_dim(const lvsr_model* m);
+int lvsr_encoder_forward(lvsr_model* m, const float* recordings_dev, const float* mask_dev,
+                         int32_t T, int32_t B, float* attended_dev, float* attended_mask_dev,
+                         void* stream);
+
+/* attention.preprocess: lvsr/bricks/attention.py:228-230. attended [T',U,E] -> [T',U,M]. */
+int lvsr_preprocess(lvsr_model* m, const float* attended_dev, int32_t Tp, int32_t U,
+                    float* preprocessed_dev, void* stream);
+
+/* ---- teacher-forced decoder: generator.cost_matrix --------------------------------
+ * (libs/blocks/blocks/bricks/sequence_generators.py:254-326).
+ * labels int64 [L,B]; labels_mask [L,B] or NULL.  Outputs: costs [L,B]; optional (NULL to
+ * skip) weights [L,B,T'], energies [L,B,T'], states [L,B,C] (= s_{i-1}),
+ * weighted_averages [L,B,E]. */
+int lvsr_cost_matrix(lvsr_model* m, const float* attended_dev, const float* attended_mask_dev,
+                     int32_t Tp, int32_t B, const int64_t* labels_dev, const float* labels_mask_dev,
+                     int32_t L, float* costs_dev, float* weights_dev, float* energies_dev,
+                     float* states_dev, float* weighted_averages_dev, void* stream);
+
+/* ---- the BeamSearch state functions (libs/blocks/blocks/search.py:101-142) ---------
+ * R rows (beam hypotheses); row r attends utterance row_utt[r] of `attended` [T',U,E]
+ * (row_utt NULL = identity, U == R: the reference's replicated-context call).
+ * `preprocessed` may be NULL: it is then recomputed, as the reference does on every call. */
+int lvsr_initial_states(lvsr_model* m, int32_t Tp, int32_t R, float* states_dev, int64_t* outputs_dev,
+                        float* weighted_averages_dev, float* weights_dev, float* energies_dev,
+                        int64_t* step_dev, void* stream);
+int lvsr_logprobs(lvsr_model* m, const float* attended_dev, const float* preprocessed_dev,
+                  const float* attended_mask_dev, int32_t Tp, int32_t U, const int32_t* row_utt_dev,
+                  int32_t R, const float* states_dev, const float* weights_dev, const int64_t* step_dev,
+                  float* neg_logprobs_dev, void* stream);
+int lvsr_next_states(lvsr_model* m, const float* attended_dev, const float* preprocessed_dev,
+                     const float* attended_mask_dev, int32_t Tp, int32_t U, const int32_t* row_utt_dev,
+                     int32_t R, const float* states_dev, const float* weights_dev, const int64_t* step_dev,
+                     const int64_t* outputs_dev, float* next_states_dev, float* next_weighted_averages_dev,
+                     float* next_weights_dev, float* next_energies_dev, int64_t* next_step_dev,
+                     void* stream);
+
+/* ---- host-buffer entry points (the call a user of the reference makes) -------------
+ * SpeechRecognizer.cost on a batch (lvsr/bricks/recognizer.py:375-390): H2D copies,
+ * encoder, cost_matrix, D2H of costs [L,B]; synchronises.  Buffers should be pinned. */
+int lvsr_recognizer_cost_host(lvsr_model* m, const float* recordings_host, const float* mask_host,
+                              const int64_t* labels_host, const float* labels_mask_host,
+                              int32_t T, int32_t B, int32_t L, float* costs_host, void* stream);
+
+/* Counters for bench.py: number of kernels this library launched since the last reset. */
+int64_t lvsr_launch_count(int reset);
+
+/* Per-kernel-class device timing (CUDA events recorded on the launching stream around every
+ * launch of that class) -- the analogue of the reference's Theano ProfileStats
+ * (libs/Theano/theano/compile/profiling.py:97).  Classes: "gemm", "bigru", "attention",
+ * "window", "dense", "readout".  lvsr_profile_read synchronises the device, returns the
+ * summed milliseconds and launch count recorded since the last read of that class. */
+int lvsr_profile_enable(int on);
+int lvsr_profile_read(const char* kernel_class, double* total_ms, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVSR_B200_H */

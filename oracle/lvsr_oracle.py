@@ -138,7 +138,8 @@ def gru_scan(inputs, gate_inputs, mask, p, reverse=False, initial_state=None,
 
 def linear(x, W, b=None):
     """B/bricks/simple.py:73-76."""
-    y = x.dot(W)
+    # 2-D BLAS product (numpy's N-D dot falls off the gemm path)
+    y = np.ascontiguousarray(x).reshape(-1, x.shape[-1]).dot(W).reshape(x.shape[:-1] + (W.shape[1],))
     if b is not None:
         y = y + b
     return y
@@ -157,7 +158,8 @@ def make_config(num_features=40, dims_bidir=(256, 256, 256, 256), subsample=None
                 num_phonemes=32, post_merge_dims=None, maxout_pieces=2,
                 dim_output_embedding=None, prior=None, energy_normalizer="softmax",
                 attention_type="content_and_conv", eos_label=None,
-                max_decoded_length_scale=1.0, use_states_for_readout=True):
+                max_decoded_length_scale=1.0, use_states_for_readout=True,
+                post_merge_activation=None):
     """The subset of ``config['net']`` the hot path depends on
     (lvsr/bricks/recognizer.py:176-204)."""
     dims_bidir = list(dims_bidir)
@@ -170,8 +172,8 @@ def make_config(num_features=40, dims_bidir=(256, 256, 256, 256), subsample=None
         conv_n=int(conv_n), conv_num_filters=int(conv_num_filters),
         num_phonemes=int(num_phonemes),
         post_merge_dims=list(post_merge_dims) if post_merge_dims else [int(dim_dec)],
-        maxout_pieces=int(maxout_pieces),   # 1 => Rectifier-like handled via 'post_merge_activation'
-        post_merge_activation="maxout" if maxout_pieces > 1 else "relu",
+        maxout_pieces=int(maxout_pieces) if (post_merge_activation in (None, "maxout")) else 1,
+        post_merge_activation=(post_merge_activation or ("maxout" if maxout_pieces > 1 else "relu")),
         dim_feedback=int(dim_output_embedding if dim_output_embedding is not None else dim_dec),
         prior=dict(prior) if prior else dict(DEFAULT_PRIOR),
         energy_normalizer=energy_normalizer or "softmax",
@@ -490,10 +492,15 @@ def readout(cfg, params, states, weighted_averages):
     if cfg["use_states_for_readout"]:
         r = r + states.dot(params[_GEN + "/readout/merge/transform_states.W"])
     r = r + params[_GEN + "/readout/post_merge/bias.b"]
-    if cfg["post_merge_activation"] == "maxout":
+    act = cfg["post_merge_activation"]
+    if act == "maxout":
         r = maxout(r, cfg["maxout_pieces"])
-    else:
+    elif act == "relu":
         r = np.maximum(r, 0)
+    elif act == "tanh":            # the reference default, lvsr/bricks/recognizer.py:206-207
+        r = np.tanh(r)
+    elif act != "identity":
+        raise ValueError(act)
     return linear(r, params[_GEN + "/readout/post_merge/mlp/linear_0.W"],
                   params[_GEN + "/readout/post_merge/mlp/linear_0.b"])
 
