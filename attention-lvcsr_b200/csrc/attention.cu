@@ -124,7 +124,7 @@ __host__ __device__ inline size_t att_smem_floats(int M, int E, int K, int n, in
 }
 
 template <int KP>
-__global__ void __launch_bounds__(ATT_THREADS, 1) att_step_kernel(AttStepArgs a, int tc_cap) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) att_step_kernel(AttStepArgs a, int tc_cap) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = (int)cluster.num_blocks();
@@ -260,10 +260,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) att_step_kernel(AttStepArgs a,
         }
 #pragma unroll
         for (int tt = 0; tt < TT; ++tt) {
-          eacc[tt] = fmaf(v4.x, tanhf_acc(mt[tt][0]), eacc[tt]);
-          eacc[tt] = fmaf(v4.y, tanhf_acc(mt[tt][1]), eacc[tt]);
-          eacc[tt] = fmaf(v4.z, tanhf_acc(mt[tt][2]), eacc[tt]);
-          eacc[tt] = fmaf(v4.w, tanhf_acc(mt[tt][3]), eacc[tt]);
+          eacc[tt] = fmaf(v4.x, fast_tanh(mt[tt][0]), eacc[tt]);
+          eacc[tt] = fmaf(v4.y, fast_tanh(mt[tt][1]), eacc[tt]);
+          eacc[tt] = fmaf(v4.z, fast_tanh(mt[tt][2]), eacc[tt]);
+          eacc[tt] = fmaf(v4.w, fast_tanh(mt[tt][3]), eacc[tt]);
         }
       }
 #pragma unroll
@@ -458,7 +458,7 @@ int attention_step(const AttStepArgs& a, cudaStream_t stream) {
   // cluster size: split a row's window over as many CTAs as keeps R*cs within one wave
   int cs = 1;
   const int sms = num_sms();
-  while (cs < 8 && a.R * cs * 2 <= sms && ceil_div(a.Tp, cs * 2) >= 16) cs *= 2;
+  while (cs < 8 && a.R * cs * 2 <= 2 * sms && ceil_div(a.Tp, cs * 2) >= 16) cs *= 2;   // two CTAs per SM
   if (a.K == 10) return launch_att<10>(a, cs, stream);
   if (a.K <= 4) return launch_att<4>(a, cs, stream);
   if (a.K <= 8) return launch_att<8>(a, cs, stream);

@@ -11,13 +11,16 @@
 //     one direction; clusters never talk to each other (no grid-wide barrier).
 //   * inside a cluster the hidden units are split: CTA `rank` owns UC = D/CS units and
 //     keeps its slice of state_to_gates / state_to_state IN REGISTERS for the whole
-//     sequence (D=256: 96 weights per thread) -- weights are read from HBM once.
-//   * per step: gates for the owned units (needs all of h), all-gather of h*r through
-//     distributed shared memory, candidate for the owned units, all-gather of h'.
-//     Two cluster barriers per step; h never leaves the chip.
-//   * each warp splits K over its 32 lanes and finishes with a halving
-//     reduce-scatter (62 shuffles instead of 320 butterflies for 64 partial sums).
-//   * the fork pre-activations of step t are prefetched into registers one step ahead.
+//     sequence -- weights are read from HBM once per layer.
+//   * per step: gates for the owned units (needs all of h), all-gather of h*r, candidate
+//     for the owned units, all-gather of h'.  Each all-gather is CS bulk DSMEM copies
+//     (cp.async.bulk shared::cta -> shared::cluster, 1 KB each) that complete on the
+//     RECEIVER's mbarrier (complete_tx): no fence, no cluster barrier in the loop; the
+//     consumer simply waits for RB*D*4 bytes to land.  h never leaves the chip.
+//   * each warp splits K over its 32 lanes and finishes with a halving reduce-scatter.
+//   * the fork pre-activations of step t+1 are prefetched into registers during step t.
+// r1a -> r1b: 4-byte remote stores + barrier.cluster.arrive.release cost 30 % of the
+// kernel in the fence (profiles/r1a_summary.md); replaced by the scheme above.
 #include "kernels.h"
 
 namespace lvsr {
@@ -25,21 +28,53 @@ namespace lvsr {
 namespace {
 
 constexpr int RB = 8;        // batch rows per cluster
-constexpr int NWARP = 8;     // warps per CTA
+constexpr int NWARP = 16;    // warps per CTA
 
-__device__ __forceinline__ void cluster_arrive() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void cluster_wait() {
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, int rank, float v) {
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, int rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(remote), "f"(v) : "memory");
+  return remote;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned long long spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1ull << 24)) __trap();   // a lost transfer must fail the launch, not hang the GPU
+  }
+}
+// local shared memory -> shared memory of CTA `rank`, completes on that CTA's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_local, uint32_t src_local, uint32_t bytes,
+                                                uint32_t bar_local, int rank) {
+  const uint32_t dst = map_to_rank(dst_local, rank);
+  const uint32_t bar = map_to_rank(bar_local, rank);
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+      "r"(src_local), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 
 // D: hidden units per direction; CS: CTAs per cluster.
@@ -48,15 +83,22 @@ __global__ void __launch_bounds__(NWARP * 32, 1)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
   constexpr int KPL = D / 32;         // k values per lane
+  constexpr int KG = KPL / 4;         // float4 groups per lane; group q covers k = q*128 + 4*lane .. +3
   constexpr int NC2 = UC / NWARP;     // units per warp (candidate columns)
   constexpr int NC1 = 2 * NC2;        // gate columns per warp: [z units | r units]
-  static_assert(D % (CS * NWARP) == 0 && D % 32 == 0, "unsupported D / cluster size");
-  static_assert(KPL % 4 == 0, "KPL must allow float4 loads");
+  static_assert(D % (CS * NWARP) == 0 && D % 128 == 0, "unsupported D / cluster size");
+  static_assert(128 % UC == 0 && UC % 4 == 0, "a lane's float4 group must sit inside one peer slice");
   constexpr int N1 = RB * NC1, N2 = RB * NC2;
+  constexpr uint32_t SLICE_BYTES = RB * UC * sizeof(float);
+  constexpr uint32_t FULL_BYTES = RB * D * sizeof(float);
 
-  __shared__ __align__(16) float hbuf[RB][D];    // current state, all units
-  __shared__ __align__(16) float hrbuf[RB][D];   // h * reset, all units
-  __shared__ float zbuf[RB][UC];                 // update gates of the owned units
+  // peer-major: slot p holds the [RB][UC] slice owned by CTA p -> one bulk copy per peer
+  __shared__ __align__(128) float hbuf[CS][RB][UC];     // h, all units
+  __shared__ __align__(128) float hrbuf[CS][RB][UC];    // h * reset, all units
+  __shared__ __align__(128) float stage_h[RB][UC];      // own slice of h (source of the copies)
+  __shared__ __align__(128) float stage_hr[RB][UC];     // own slice of h * reset
+  __shared__ float zbuf[RB][UC];                        // update gates of the owned units
+  __shared__ __align__(8) unsigned long long mbar[2];   // [0]: h arrivals, [1]: h*r arrivals
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cluster_id = blockIdx.x / CS;
@@ -64,7 +106,8 @@ bigru_kernel(BiGruArgs a) {
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
   const int dir = cluster_id & 1;             // 0 forward, 1 backward
   const int row0 = (cluster_id >> 1) * RB;    // first batch row of this cluster
-  const int u_warp = rank * UC + warp * NC2;  // first unit owned by this warp
+  const int ul_warp = warp * NC2;             // first owned unit of this warp, local index
+  const int u_warp = rank * UC + ul_warp;     // ... global unit index
 
   const float* Wg = dir ? a.Wg_b : a.Wg_f;    // [D, 2D]  cols [update | reset]
   const float* Ws = dir ? a.Ws_b : a.Ws_f;    // [D, D]
@@ -73,21 +116,31 @@ bigru_kernel(BiGruArgs a) {
   // ---- weights -> registers (once) -------------------------------------------------
   float w1[NC1][KPL], w2[NC2][KPL];
 #pragma unroll
-  for (int c = 0; c < NC1; ++c) {
-    const int col = (c < NC2) ? (u_warp + c) : (D + u_warp + (c - NC2));
+  for (int kk = 0; kk < KPL; ++kk) {
+    const int k = (kk / 4) * 128 + 4 * lane + (kk % 4);
 #pragma unroll
-    for (int kk = 0; kk < KPL; ++kk) w1[c][kk] = Wg[(long long)(lane * KPL + kk) * (2 * D) + col];
+    for (int c = 0; c < NC1; ++c) {
+      const int col = (c < NC2) ? (u_warp + c) : (D + u_warp + (c - NC2));
+      w1[c][kk] = Wg[(long long)k * (2 * D) + col];
+    }
+#pragma unroll
+    for (int c = 0; c < NC2; ++c) w2[c][kk] = Ws[(long long)k * D + u_warp + c];
   }
-#pragma unroll
-  for (int c = 0; c < NC2; ++c)
-#pragma unroll
-    for (int kk = 0; kk < KPL; ++kk) w2[c][kk] = Ws[(long long)(lane * KPL + kk) * D + u_warp + c];
 
-  for (int i = tid; i < RB * D; i += NWARP * 32) hbuf[i / D][i % D] = h0[i % D];
+  for (int i = tid; i < RB * D; i += NWARP * 32) {
+    const int r = i / D, u = i % D;
+    hbuf[u / UC][r][u % UC] = h0[u];
+  }
+  for (int i = tid; i < RB * UC; i += NWARP * 32) stage_h[i / UC][i % UC] = h0[rank * UC + (i % UC)];
 
-  // which reduced outputs this lane ends up owning (static per kernel)
-  // phase 1: N1 values -> N1/32 (>=1) per lane; flattened index = row * NC1 + c
-  // phase 2: N2 values -> N2/32 (>=1) per lane; flattened index = row * NC2 + c
+  const uint32_t bar_h = smem_u32(&mbar[0]), bar_hr = smem_u32(&mbar[1]);
+  if (tid == 0) {
+    mbar_init(bar_h, 1);
+    mbar_init(bar_hr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+
+  // reduced outputs owned by this lane: phase 1 flattened idx = row*NC1 + c, phase 2 = row*NC2 + c
   constexpr int O1 = (N1 >= 32) ? N1 / 32 : 1;
   constexpr int O2 = (N2 >= 32) ? N2 / 32 : 1;
   constexpr int DUP1 = (N1 >= 32) ? 1 : 32 / N1;   // lanes holding the same value
@@ -99,7 +152,6 @@ bigru_kernel(BiGruArgs a) {
   const long long pre_ld = 6LL * D;                       // [A | Gz | Gr] per direction
   const float* pre_dir = a.pre + (long long)dir * 3 * D;
 
-  // prefetch registers for the current step
   float pg[O1], pa[O2], pm[O2];
   auto prefetch = [&](int t) {
 #pragma unroll
@@ -107,27 +159,30 @@ bigru_kernel(BiGruArgs a) {
       const int idx = base1 + j, row = idx / NC1, c = idx % NC1;
       const int b = row0 + row;
       const int col = (c < NC2) ? (D + u_warp + c) : (2 * D + u_warp + (c - NC2));
-      pg[j] = (b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + col) : 0.f;
+      pg[j] = (act1 && b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + col) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < O2; ++j) {
       const int idx = base2 + j, row = idx / NC2, c = idx % NC2;
       const int b = row0 + row;
-      pa[j] = (b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + u_warp + c) : 0.f;
-      pm[j] = (b < B && a.mask) ? __ldg(a.mask + (long long)t * a.mask_tstride + b) : 1.f;
+      pa[j] = (act2 && b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + u_warp + c) : 0.f;
+      pm[j] = (act2 && b < B && a.mask) ? __ldg(a.mask + (long long)t * a.mask_tstride + b) : 1.f;
     }
   };
 
-  // all CTAs of the cluster must be resident before any remote shared-memory write
+  // every CTA of the cluster must be resident (and its mbarriers initialised) before any
+  // remote copy is issued
   __syncthreads();
-  cluster_arrive();
-  cluster_wait();
+  cluster_sync_all();
 
-  const uint32_t hr_base = smem_u32(&hrbuf[0][0]);
-  const uint32_t h_base = smem_u32(&hbuf[0][0]);
+  const uint32_t hbuf_mine = smem_u32(&hbuf[rank][0][0]);     // same offset in every peer: slot `rank`
+  const uint32_t hrbuf_mine = smem_u32(&hrbuf[rank][0][0]);
+  const uint32_t stage_h_a = smem_u32(&stage_h[0][0]), stage_hr_a = smem_u32(&stage_hr[0][0]);
 
   int t = dir ? (T - 1) : 0;
   const int dt = dir ? -1 : 1;
+  int sub_phase = dir ? ((T - 1) % a.subsample) : 0;   // t % subsample, maintained incrementally
+  int t_out = t / a.subsample;
   prefetch(t);
 
   for (int s = 0; s < T; ++s, t += dt) {
@@ -138,14 +193,22 @@ bigru_kernel(BiGruArgs a) {
     for (int j = 0; j < O2; ++j) { a_cur[j] = pa[j]; m_cur[j] = pm[j]; }
     if (s + 1 < T) prefetch(t + dt);
 
+    // h(s-1) from all peers has landed (step 0 uses the locally initialised h0)
+    if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
+    if (tid == 0) {
+      mbar_arm(bar_h, FULL_BYTES);    // arrivals of h'(s)
+      mbar_arm(bar_hr, FULL_BYTES);   // arrivals of (h*r)(s)
+    }
+
     // ---- phase 1: gates of the owned units -----------------------------------------
     float acc1[N1];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       float hv[KPL];
 #pragma unroll
-      for (int q = 0; q < KPL / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(&hbuf[r][lane * KPL + q * 4]);
+      for (int q = 0; q < KG; ++q) {
+        const int k0 = q * 128 + 4 * lane;
+        const float4 v = *reinterpret_cast<const float4*>(&hbuf[k0 / UC][r][k0 % UC]);
         hv[q * 4 + 0] = v.x; hv[q * 4 + 1] = v.y; hv[q * 4 + 2] = v.z; hv[q * 4 + 3] = v.w;
       }
 #pragma unroll
@@ -161,29 +224,29 @@ bigru_kernel(BiGruArgs a) {
 #pragma unroll
       for (int j = 0; j < O1; ++j) {
         const int idx = base1 + j, row = idx / NC1, c = idx % NC1;
-        const float gate = sigmoidf_acc(acc1[j] + g_cur[j]);
+        const float gate = fast_sigmoid(acc1[j] + g_cur[j]);
         if (c < NC2) {
-          zbuf[row][warp * NC2 + c] = gate;
+          zbuf[row][ul_warp + c] = gate;
         } else {
-          const int u = u_warp + (c - NC2);
-          const float hr = hbuf[row][u] * gate;
-          const uint32_t addr = hr_base + (uint32_t)((row * D + u) * sizeof(float));
-#pragma unroll
-          for (int pr = 0; pr < CS; ++pr) st_cluster_f32(addr, pr, hr);
+          const int ul = ul_warp + (c - NC2);
+          stage_hr[row][ul] = stage_h[row][ul] * gate;
         }
       }
     }
-    cluster_arrive();
-    cluster_wait();
+    fence_async_smem();          // generic-proxy writes of stage_hr -> visible to the bulk-copy engine
+    __syncthreads();
+    if (warp == 0 && lane < CS) dsmem_bulk_copy(hrbuf_mine, stage_hr_a, SLICE_BYTES, bar_hr, lane);
 
     // ---- phase 2: candidate + blend for the owned units ----------------------------
+    mbar_wait(bar_hr, (uint32_t)(s & 1));
     float acc2[N2];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       float hv[KPL];
 #pragma unroll
-      for (int q = 0; q < KPL / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[r][lane * KPL + q * 4]);
+      for (int q = 0; q < KG; ++q) {
+        const int k0 = q * 128 + 4 * lane;
+        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[k0 / UC][r][k0 % UC]);
         hv[q * 4 + 0] = v.x; hv[q * 4 + 1] = v.y; hv[q * 4 + 2] = v.z; hv[q * 4 + 3] = v.w;
       }
 #pragma unroll
@@ -199,24 +262,40 @@ bigru_kernel(BiGruArgs a) {
 #pragma unroll
       for (int j = 0; j < O2; ++j) {
         const int idx = base2 + j, row = idx / NC2, c = idx % NC2;
-        const int u = u_warp + c;
-        const float cand = tanhf_acc(acc2[j] + a_cur[j]);
-        const float z = zbuf[row][warp * NC2 + c];
-        const float hold = hbuf[row][u];
+        const int ul = ul_warp + c;
+        const float cand = fast_tanh(acc2[j] + a_cur[j]);
+        const float z = zbuf[row][ul];
+        const float hold = stage_h[row][ul];
         float hn = cand * z + hold * (1.f - z);
         hn = m_cur[j] * hn + (1.f - m_cur[j]) * hold;
-        const uint32_t addr = h_base + (uint32_t)((row * D + u) * sizeof(float));
-#pragma unroll
-        for (int pr = 0; pr < CS; ++pr) st_cluster_f32(addr, pr, hn);
+        stage_h[row][ul] = hn;
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (warp == 0 && lane < CS) dsmem_bulk_copy(hbuf_mine, stage_h_a, SLICE_BYTES, bar_h, lane);
+    if (sub_phase == 0 && warp >= 1 && warp <= 2) {
+      // coalesced store of the owned slice: RB rows x UC floats (128 B per row)
+      constexpr int F4 = RB * UC / 4;
+      for (int i = (warp - 1) * 32 + lane; i < F4; i += 64) {
+        const int row = i / (UC / 4), c4 = i % (UC / 4);
         const int b = row0 + row;
-        if (b < B && (t % a.subsample) == 0) {
-          a.out[((long long)(t / a.subsample) * B + b) * (2 * D) + dir * D + u] = hn;
+        if (b < B) {
+          const float4 v = *reinterpret_cast<const float4*>(&stage_h[row][c4 * 4]);
+          *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + b) * (2 * D) + dir * D + rank * UC + c4 * 4) = v;
         }
       }
     }
-    cluster_arrive();
-    cluster_wait();
+    // advance t % subsample and t / subsample without dividing
+    if (dir == 0) {
+      if (++sub_phase == a.subsample) { sub_phase = 0; ++t_out; }
+    } else {
+      if (sub_phase == 0) { sub_phase = a.subsample - 1; --t_out; } else { --sub_phase; }
+    }
   }
+  // drain: the last h' copies must have landed everywhere before any CTA may exit
+  mbar_wait(bar_h, (uint32_t)((T - 1) & 1));
+  cluster_sync_all();
 }
 
 template <int D, int CS>

@@ -62,6 +62,10 @@ __device__ __forceinline__ float tanhf_acc(float x) {
   return copysignf(t, x);
 }
 
+// 2-MUFU activations (ex2 + rcp): |abs err| ~ 2e-7; saturate correctly at +-inf
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
