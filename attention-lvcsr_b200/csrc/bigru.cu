@@ -27,8 +27,11 @@ namespace lvsr {
 
 namespace {
 
-constexpr int RB = 8;        // batch rows per cluster
-constexpr int NWARP = 16;    // warps per CTA
+// Two CTAs are co-resident per SM (256 threads, <=128 registers each): they belong to
+// different clusters, i.e. independent recurrences, so one chain's exchange latency is
+// covered by the other chain's arithmetic.
+constexpr int RB = 4;        // batch rows per cluster
+constexpr int NWARP = 8;     // warps per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -79,7 +82,7 @@ __device__ __forceinline__ void fence_async_smem() {
 
 // D: hidden units per direction; CS: CTAs per cluster.
 template <int D, int CS>
-__global__ void __launch_bounds__(NWARP * 32, 1)
+__global__ void __launch_bounds__(NWARP * 32, 2)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
   constexpr int KPL = D / 32;         // k values per lane
@@ -98,6 +101,10 @@ bigru_kernel(BiGruArgs a) {
   __shared__ __align__(128) float stage_h[RB][UC];      // own slice of h (source of the copies)
   __shared__ __align__(128) float stage_hr[RB][UC];     // own slice of h * reset
   __shared__ float zbuf[RB][UC];                        // update gates of the owned units
+  // state_to_state slice: [warp][kk][lane][c] so a lane fetches its NC2 columns of one k as
+  // one vector; reloaded into registers at the start of every candidate phase (the gate
+  // accumulators are dead by then), which keeps the kernel at two CTAs per SM
+  __shared__ __align__(16) float w2s[NWARP][KPL][32][NC2];
   __shared__ __align__(8) unsigned long long mbar[2];   // [0]: h arrivals, [1]: h*r arrivals
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,7 +121,7 @@ bigru_kernel(BiGruArgs a) {
   const float* h0 = dir ? a.h0_b : a.h0_f;    // [D]
 
   // ---- weights -> registers (once) -------------------------------------------------
-  float w1[NC1][KPL], w2[NC2][KPL];
+  float w1[NC1][KPL];
 #pragma unroll
   for (int kk = 0; kk < KPL; ++kk) {
     const int k = (kk / 4) * 128 + 4 * lane + (kk % 4);
@@ -124,7 +131,7 @@ bigru_kernel(BiGruArgs a) {
       w1[c][kk] = Wg[(long long)k * (2 * D) + col];
     }
 #pragma unroll
-    for (int c = 0; c < NC2; ++c) w2[c][kk] = Ws[(long long)k * D + u_warp + c];
+    for (int c = 0; c < NC2; ++c) w2s[warp][kk][lane][c] = Ws[(long long)k * D + u_warp + c];
   }
 
   for (int i = tid; i < RB * D; i += NWARP * 32) {
@@ -238,6 +245,11 @@ bigru_kernel(BiGruArgs a) {
     if (warp == 0 && lane < CS) dsmem_bulk_copy(hrbuf_mine, stage_hr_a, SLICE_BYTES, bar_hr, lane);
 
     // ---- phase 2: candidate + blend for the owned units ----------------------------
+    float w2[NC2][KPL];
+#pragma unroll
+    for (int kk = 0; kk < KPL; ++kk)
+#pragma unroll
+      for (int c = 0; c < NC2; ++c) w2[c][kk] = w2s[warp][kk][lane][c];
     mbar_wait(bar_hr, (uint32_t)(s & 1));
     float acc2[N2];
 #pragma unroll
@@ -274,10 +286,10 @@ bigru_kernel(BiGruArgs a) {
     fence_async_smem();
     __syncthreads();
     if (warp == 0 && lane < CS) dsmem_bulk_copy(hbuf_mine, stage_h_a, SLICE_BYTES, bar_h, lane);
-    if (sub_phase == 0 && warp >= 1 && warp <= 2) {
+    if (sub_phase == 0 && warp == 1) {
       // coalesced store of the owned slice: RB rows x UC floats (128 B per row)
       constexpr int F4 = RB * UC / 4;
-      for (int i = (warp - 1) * 32 + lane; i < F4; i += 64) {
+      for (int i = lane; i < F4; i += 32) {
         const int row = i / (UC / 4), c4 = i % (UC / 4);
         const int b = row0 + row;
         if (b < B) {
