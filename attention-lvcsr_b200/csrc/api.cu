@@ -6,6 +6,7 @@
 #include "lvsr_b200.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -133,6 +134,7 @@ struct lvsr_model {
   // packed, kernel-side weights (rebuilt by finalize)
   std::vector<float*> Wcat, bcat;   // per encoder layer: [Din, 6D], [6D]
   float* Wd_cat = nullptr;          // [E, 3C] = [distribute gate_inputs (2C) | distribute inputs (C)]
+  float* Wb1 = nullptr;             // [E+C, 3C] = Wd_cat stacked on [state_to_gates | 0] (persistent decoder)
   float* Wff_cat = nullptr;         // [Cfb, 3C] = [fork gate_inputs | fork inputs]
   float* bff_cat = nullptr;         // [3C]
   float* FF = nullptr;              // [(V+1), 3C] = lookup . Wff_cat + bff_cat
@@ -386,8 +388,9 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
     LVSR_CHECK(bigru_supported(cfg->dims_bidir[l]), "encoder dim %d unsupported (128 or 256)", cfg->dims_bidir[l]);
     LVSR_CHECK(cfg->subsample[l] >= 1, "subsample must be >= 1");
   }
-  LVSR_CHECK(cfg->dim_dec % 8 == 0 && cfg->dim_matcher % 8 == 0 && cfg->post_merge_dim % 8 == 0,
-             "dim_dec, dim_matcher and post_merge_dim must be multiples of 8");
+  LVSR_CHECK(cfg->dim_dec % 8 == 0 && cfg->post_merge_dim % 8 == 0, "dim_dec and post_merge_dim must be multiples of 8");
+  LVSR_CHECK(cfg->dim_matcher == 128 || cfg->dim_matcher == 256 || cfg->dim_matcher == 512,
+             "dim_matcher %d unsupported by the attention kernel (128, 256 or 512)", cfg->dim_matcher);
   LVSR_CHECK(cfg->dim_feedback % 4 == 0, "dim_feedback must be a multiple of 4");
   LVSR_CHECK(cfg->maxout_pieces >= 1 && cfg->post_merge_dim % cfg->maxout_pieces == 0, "bad maxout_pieces");
   LVSR_CHECK(cfg->post_merge_activation >= LVSR_ACT_MAXOUT && cfg->post_merge_activation <= LVSR_ACT_IDENTITY,
@@ -422,6 +425,7 @@ int lvsr_model_destroy(lvsr_model* m) {
   for (float* p : m->Wcat) if (p) cudaFree(p);
   for (float* p : m->bcat) if (p) cudaFree(p);
   if (m->Wd_cat) cudaFree(m->Wd_cat);
+  if (m->Wb1) cudaFree(m->Wb1);
   if (m->Wff_cat) cudaFree(m->Wff_cat);
   if (m->bff_cat) cudaFree(m->bff_cat);
   if (m->FF) cudaFree(m->FF);
@@ -479,6 +483,7 @@ int lvsr_model_finalize(lvsr_model* m) {
     }
     const int C = c.dim_dec;
     LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wd_cat), (size_t)m->E * 3 * C * sizeof(float)));
+    LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wb1), (size_t)(m->E + C) * 3 * C * sizeof(float)));
     LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wff_cat), (size_t)c.dim_feedback * 3 * C * sizeof(float)));
     LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->bff_cat), (size_t)3 * C * sizeof(float)));
     LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->FF), (size_t)(c.num_phonemes + 1) * 3 * C * sizeof(float)));
@@ -501,6 +506,9 @@ int lvsr_model_finalize(lvsr_model* m) {
   // decoder-side packing: gate columns first (update | reset), then the candidate inputs
   if (int rc = copy_cols(m->Wd_cat, 3 * C, 0, m->P(t + "/distribute/fork_gate_inputs.W"), m->E, 2 * C, st)) return rc;
   if (int rc = copy_cols(m->Wd_cat, 3 * C, 2 * C, m->P(t + "/distribute/fork_inputs.W"), m->E, C, st)) return rc;
+  LVSR_CUDA_OK(cudaMemsetAsync(m->Wb1, 0, (size_t)(m->E + C) * 3 * C * sizeof(float), st));
+  if (int rc = copy_cols(m->Wb1, 3 * C, 0, m->Wd_cat, m->E, 3 * C, st)) return rc;
+  if (int rc = copy_cols(m->Wb1 + (size_t)m->E * 3 * C, 3 * C, 0, m->P(t + "/transition.state_to_gates"), C, 2 * C, st)) return rc;
   if (int rc = copy_cols(m->Wff_cat, 3 * C, 0, m->P(g + "/fork/fork_gate_inputs.W"), Cfb, 2 * C, st)) return rc;
   if (int rc = copy_cols(m->Wff_cat, 3 * C, 2 * C, m->P(g + "/fork/fork_inputs.W"), Cfb, C, st)) return rc;
   if (int rc = copy_cols(m->bff_cat, 3 * C, 0, m->P(g + "/fork/fork_gate_inputs.b"), 1, 2 * C, st)) return rc;
@@ -603,8 +611,70 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
   if (int rc = onehot_rows(w0, B, Tp, st)) return rc;                               // lvsr/bricks/attention.py:215-222
   if (int rc = fill_f32(costs, (long long)L * B, 0.f, st)) return rc;
 
+  bool scanned = false;
+  if (getenv("LVSR_NO_DEC_SCAN") == nullptr) {
+    DecScanArgs d = {};
+    d.P = P; d.H = attended; d.maskH = attended_mask;
+    d.filt = m->P(std::string(ATT) + "/conv1d.filters");
+    d.Wh = m->P(std::string(ATT) + "/handler.W");
+    d.v = m->P(std::string(ATT) + "/energy_comp/linear.W");
+    d.v_bias = m->v_bias;
+    d.prior = prior_of(c);
+    d.Wb1 = m->Wb1;
+    d.Wstate = m->P(std::string(TR) + "/transition.state_to_state");
+    d.Ws = m->P(std::string(ATT) + "/state_trans/transform_states.W");
+    d.FF = m->FF;
+    d.labels = lab; d.lmask = labels_mask;
+    d.s_all = s_all; d.ctx_all = ctx_all; d.w0 = w0;
+    d.w_seq = weights_out; d.w_pp[0] = wpp[0]; d.w_pp[1] = wpp[1];
+    d.e_seq = energies_out; d.e_scratch = e_scratch;
+    d.Tp = Tp; d.B = B; d.L = L; d.M = M; d.E = E; d.C = C; d.K = c.conv_num_filters; d.n = c.conv_n;
+    d.normalizer = c.energy_normalizer;
+    d.q = ws.f32((size_t)B * M);
+    d.z = ws.f32((size_t)B * C);
+    d.hr = ws.f32((size_t)B * C);
+    d.ai = ws.f32((size_t)B * C);
+    d.rowpos = ws.f32((size_t)2 * B);
+    d.bar = reinterpret_cast<unsigned*>(ws.i32(4));
+    LVSR_CHECK(d.q && d.z && d.hr && d.ai && d.rowpos && d.bar, "out of device memory (decoder scan workspace)");
+    if (int rc = fill_f32(d.rowpos, 2 * B, 0.f, st)) return rc;
+    const bool trace = getenv("LVSR_DEC_TRACE") != nullptr;
+    if (trace) {
+      d.trace = reinterpret_cast<unsigned long long*>(ws.i64((size_t)2 * L * 9 + (size_t)L * 8));
+      LVSR_CUDA_OK(cudaMemsetAsync(d.trace, 0, ((size_t)2 * L * 9 + (size_t)L * 8) * 8, st));
+    }
+    int supported = 0;
+    if (int rc = dec_scan_try(d, &supported, st)) return rc;
+    scanned = supported != 0;
+    if (trace && scanned) {
+      std::vector<unsigned long long> h((size_t)2 * L * 9 + (size_t)L * 8);
+      LVSR_CUDA_OK(cudaMemcpyAsync(h.data(), d.trace, h.size() * 8, cudaMemcpyDeviceToHost, st));
+      LVSR_CUDA_OK(cudaStreamSynchronize(st));
+      const char* names[8] = {"A", "syncA", "B1", "sync1", "B2", "sync2", "B3", "sync3"};
+      for (int slot = 0; slot < 2; ++slot) {
+        double sum[8] = {0};
+        int n = 0;
+        for (int i = 1; i + 1 < L; ++i, ++n)
+          for (int j = 0; j < 8; ++j) sum[j] += (double)(h[((size_t)slot * L + i) * 9 + j + 1] - h[((size_t)slot * L + i) * 9 + j]);
+        fprintf(stderr, "[dec_scan trace] CTA %s:", slot == 0 ? "first" : "last");
+        for (int j = 0; j < 8; ++j) fprintf(stderr, " %s=%.2fus", names[j], n ? sum[j] / n * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+      }
+      {
+        const char* an[7] = {"stage", "conv", "energy", "stats", "ctx", "exchange", "combine"};
+        double sum[7] = {0};
+        int n = 0;
+        for (int i = 1; i + 1 < L; ++i, ++n)
+          for (int j = 0; j < 7; ++j)
+            sum[j] += (double)(h[(size_t)2 * L * 9 + (size_t)i * 8 + j + 1] - h[(size_t)2 * L * 9 + (size_t)i * 8 + j]);
+        fprintf(stderr, "[dec_scan trace] attention row 0:");
+        for (int j = 0; j < 7; ++j) fprintf(stderr, " %s=%.2fus", an[j], n ? sum[j] / n * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   const float* w_prev = w0;
-  for (int i = 0; i < L; ++i) {
+  for (int i = 0; i < L && !scanned; ++i) {
     float* w_i = weights_out ? weights_out + (size_t)i * B * Tp : wpp[i & 1];
     float* e_i = energies_out ? energies_out + (size_t)i * B * Tp : e_scratch;
     float* ctx_i = ctx_all + (size_t)i * B * E;

@@ -1,0 +1,475 @@
+// Persistent teacher-forced decoder: ONE cooperative kernel runs all L steps of
+// AttentionRecurrent.do_apply (libs/blocks/blocks/bricks/attention.py:668-707) for the
+// whole batch -- take_glimpses -> Distribute -> GatedRecurrent step -- i.e. the scan inside
+// BaseSequenceGenerator.evaluate (libs/blocks/blocks/bricks/sequence_generators.py:254-311).
+//
+// B200 mapping
+//   * one CTA per SM, resident for the whole sequence; the GRU / state-transform weight
+//     slices of each CTA stay in SHARED MEMORY across all steps (2.75 MB spread over the
+//     grid), as do the attention constants (conv filters, handler, energy vector).
+//   * phase A (attention) is row-parallel: a cluster of `cs` CTAs per decoder row streams the
+//     row's P and H slices once and merges (max, sum, partial context) through DSMEM.
+//   * phases B1..B3 (gates, candidate, next query) are 2-D tiled skinny products:
+//     16-row x nc-column tiles, K split over the 16 warps of the CTA, fused GRU epilogues.
+//   * phases are separated by a grid barrier (one L2 atomic per CTA + acquire poll); the
+//     window statistics of the next step (mean / median position) ride on the attention
+//     exchange, so the windowing priors need no extra pass and no host round trip.
+#include "attention_row.cuh"
+
+namespace lvsr {
+
+namespace {
+
+constexpr int DS_THREADS = ATT_NT;
+constexpr int DS_WARPS = DS_THREADS / 32;
+constexpr int DS_ROWS = 16;          // rows per dense tile
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned atom_add_acqrel_u32(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;\n" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident (cooperative launch).
+// Split-phase: grid_arrive publishes this CTA's writes (acq_rel RMW by thread 0 after the CTA
+// barrier -- release is cumulative over the barrier), grid_wait acquires everybody else's.
+// Cross-CTA data is always read with ld.global.cg (L2), so no L1 invalidation is needed.
+__device__ __forceinline__ void grid_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atom_add_acqrel_u32(&bar[0], 1u);
+    if (prev == nblocks - 1) {
+      bar[0] = 0;
+      st_release_u32(&bar[1], gen + 1);
+    }
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned* bar, unsigned& gen) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(&bar[1]) == gen) {
+      if (++spins > (1u << 23)) __trap();   // never hang the GPU on a lost CTA
+    }
+  }
+  gen++;
+  __syncthreads();
+}
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks, unsigned& gen) {
+  grid_arrive(bar, nblocks, gen);
+  grid_wait(bar, gen);
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+
+enum { EP_GATES = 0, EP_CAND = 1, EP_QUERY = 2 };
+
+struct DenseIO {
+  const float* X1; int K1;      // rows of width K1
+  const float* X2; int K2;      // appended columns (may be null)
+  int R;                        // valid rows
+  int N;                        // total output columns
+  int mode;
+  int C;
+  const float* add;             // [*, N] addend
+  const long long* arow;        // row index into add (or null: identity)
+  const float* s;               // [R, C] current state
+  float* z; float* hr; float* ai;
+  const float* rmask;           // [R] or null
+  float* out;                   // EP_CAND: next state [R, C]; EP_QUERY: q [R, N]
+};
+
+// One 16-row x (8*NQ)-column tile.  lane = ks*16 + rq*2 + cq: rows {2rq, 2rq+1}, columns
+// [cq*4NQ, +4NQ); warp w and k-half ks own the contiguous k range [(2w+ks)*Ktot/32, +Ktot/32).
+// All of a lane's x values (2 rows x Ktot/32) are requested from L2 before the first FMA:
+// one exposed L2 round trip per phase instead of one per k-block.
+template <int NQ, int KPER>
+__device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int wstride, int r0, int c0,
+                                           float* red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ks = lane >> 4, rq = (lane >> 1) & 7, cq = lane & 1;
+  constexpr int NCL = 4 * NQ;
+  constexpr int NC = 2 * NCL;
+  const int kbeg = (warp * 2 + ks) * KPER;
+  float acc[2][NCL];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NCL; ++j) acc[i][j] = 0.f;
+  float4 xv[2][KPER / 4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = min(r0 + rq * 2 + i, d.R - 1);
+#pragma unroll
+    for (int kb = 0; kb < KPER / 4; ++kb) {
+      const int k = kbeg + kb * 4;
+      const float* src = (k < d.K1) ? (d.X1 + (long long)row * d.K1 + k) : (d.X2 + (long long)row * d.K2 + (k - d.K1));
+      xv[i][kb] = __ldcg(reinterpret_cast<const float4*>(src));
+    }
+  }
+#pragma unroll
+  for (int kb = 0; kb < KPER / 4; ++kb) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* wr = ws + (size_t)(kbeg + kb * 4 + kk) * wstride + cq * NCL;
+      float wv[NCL];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + q * 4);
+        wv[q * 4 + 0] = w4.x; wv[q * 4 + 1] = w4.y; wv[q * 4 + 2] = w4.z; wv[q * 4 + 3] = w4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 x4 = xv[i][kb];
+        const float x = kk == 0 ? x4.x : kk == 1 ? x4.y : kk == 2 ? x4.z : x4.w;
+#pragma unroll
+        for (int j = 0; j < NCL; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NCL; ++j) {
+      float v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (ks == 0) red[(size_t)warp * (DS_ROWS * NC) + (rq * 2 + i) * NC + cq * NCL + j] = v;
+    }
+  __syncthreads();
+  for (int o = tid; o < DS_ROWS * NC; o += DS_THREADS) {
+    const int rl = o / NC, cl = o % NC;
+    const int r = r0 + rl, c = c0 + cl;
+    if (r >= d.R || c >= d.N) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < DS_WARPS; ++wq) v += red[(size_t)wq * (DS_ROWS * NC) + o];
+    if (d.add) {
+      const long long ar = d.arow ? d.arow[r] : (long long)r;
+      v += d.arow ? __ldg(d.add + ar * d.N + c) : __ldcg(d.add + ar * d.N + c);
+    }
+    const int C = d.C;
+    if (d.mode == EP_GATES) {
+      if (c < C) {
+        d.z[(long long)r * C + c] = fast_sigmoid(v);
+      } else if (c < 2 * C) {
+        const int uu = c - C;
+        d.hr[(long long)r * C + uu] = __ldcg(d.s + (long long)r * C + uu) * fast_sigmoid(v);
+      } else {
+        d.ai[(long long)r * C + (c - 2 * C)] = v;
+      }
+    } else if (d.mode == EP_CAND) {
+      const float cand = fast_tanh(v);
+      const float zz = __ldcg(d.z + (long long)r * C + c);
+      const float sold = __ldcg(d.s + (long long)r * C + c);
+      float sn = cand * zz + sold * (1.f - zz);
+      if (d.rmask) {
+        const float m = d.rmask[r];
+        sn = m * sn + (1.f - m) * sold;
+      }
+      d.out[(long long)r * C + c] = sn;
+    } else {
+      d.out[(long long)r * d.N + c] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// nq = (columns per CTA) / 8 in {1,2,3}; kper = Ktot / 32 in {4, 8, 12, 16, 24}
+__device__ __forceinline__ void dense_dispatch(int nq, const DenseIO& d, const float* ws, int wstride, int r0,
+                                               int c0, float* red) {
+  const int kper = (d.K1 + d.K2) / 32;
+#define DS_CASE(NQ_, KP_) \
+  if (nq == NQ_ && kper == KP_) { dense_tile<NQ_, KP_>(d, ws, wstride, r0, c0, red); return; }
+  DS_CASE(1, 4) DS_CASE(2, 4) DS_CASE(3, 4)
+  DS_CASE(1, 8) DS_CASE(2, 8) DS_CASE(3, 8)
+  DS_CASE(1, 12) DS_CASE(2, 12) DS_CASE(3, 12)
+  DS_CASE(1, 16) DS_CASE(2, 16) DS_CASE(3, 16)
+  DS_CASE(1, 24) DS_CASE(2, 24) DS_CASE(3, 24)
+#undef DS_CASE
+  __trap();   // plan() only admits the shapes above
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int bid = blockIdx.x, G = gridDim.x;
+  const int cluster_id = bid / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = a.B, C = a.C, E = a.E, M = a.M;
+
+  // ---- shared memory: [attention region][w1][w2][w3][red] -----------------------------
+  float* att = smem;
+  size_t off = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
+  off = (off + 3) & ~(size_t)3;
+  const int ws1 = a.nc1 + 4, ws2 = a.nc2 + 4, ws3 = a.nc3 + 4;
+  float* w1s = smem + off; off += (size_t)(E + C) * ws1;
+  float* w2s = smem + off; off += (size_t)C * ws2;
+  float* w3s = smem + off; off += (size_t)C * ws3;
+  off = (off + 3) & ~(size_t)3;
+  float* red = smem + off;
+
+  // dense tile of this CTA
+  const int rg = bid % a.nrg, cg_ = bid / a.nrg;
+  const int r0 = rg * DS_ROWS;
+  const bool in1 = cg_ * a.nc1 < 3 * C, in2 = cg_ * a.nc2 < C, in3 = cg_ * a.nc3 < M;
+
+  // ---- one-time staging: weight slices + attention constants -----------------------------
+  for (int i = tid; i < (E + C) * a.nc1; i += DS_THREADS) {
+    const int k = i / a.nc1, c = i % a.nc1, col = cg_ * a.nc1 + c;
+    w1s[(size_t)k * ws1 + c] = (in1 && col < 3 * C) ? a.Wb1[(long long)k * 3 * C + col] : 0.f;
+  }
+  for (int i = tid; i < C * a.nc2; i += DS_THREADS) {
+    const int k = i / a.nc2, c = i % a.nc2, col = cg_ * a.nc2 + c;
+    w2s[(size_t)k * ws2 + c] = (in2 && col < C) ? a.Wstate[(long long)k * C + col] : 0.f;
+  }
+  for (int i = tid; i < C * a.nc3; i += DS_THREADS) {
+    const int k = i / a.nc3, c = i % a.nc3, col = cg_ * a.nc3 + c;
+    w3s[(size_t)k * ws3 + c] = (in3 && col < M) ? a.Ws[(long long)k * M + col] : 0.f;
+  }
+  att_stage_constants(att_carve(att, M, E, a.K, a.n, a.tc_cap, cs), a.v, a.Wh, a.filt, M, a.K, a.n);
+  __syncthreads();
+
+  unsigned gen = 0;
+  DenseIO dq = {};   // query for the first step: q = s_0 . W_state
+  dq.X1 = a.s_all; dq.K1 = C; dq.X2 = nullptr; dq.K2 = 0; dq.R = R; dq.N = M; dq.mode = EP_QUERY; dq.C = C;
+  dq.out = a.q;
+  if (in3) dense_dispatch(a.nc3 / 8, dq, w3s, ws3, r0, cg_ * a.nc3, red);
+  cluster.sync();     // every CTA of the cluster is resident before the first DSMEM write
+  grid_sync(a.bar, G, gen);
+
+  const int trace_slot = (bid == 0) ? 0 : (bid == G - 1 ? 1 : -1);
+#define DS_STAMP(j)                                                                         \
+  do {                                                                                      \
+    if (a.trace && trace_slot >= 0 && tid == 0)                                             \
+      a.trace[((size_t)trace_slot * a.L + i) * 9 + (j)] = global_ns();                      \
+  } while (0)
+  for (int i = 0; i < a.L; ++i) {
+    DS_STAMP(0);
+    const float* w_prev = (i == 0) ? a.w0 : (a.w_seq ? a.w_seq + (size_t)(i - 1) * R * a.Tp : a.w_pp[(i - 1) & 1]);
+    float* w_cur = a.w_seq ? a.w_seq + (size_t)i * R * a.Tp : a.w_pp[i & 1];
+    float* e_cur = a.e_seq ? a.e_seq + (size_t)i * R * a.Tp : a.e_scratch;
+    float* ctx_cur = a.ctx_all + (size_t)i * R * E;
+    const float* s_cur = a.s_all + (size_t)i * R * C;
+    float* s_next = a.s_all + (size_t)(i + 1) * R * C;
+
+    // ================= phase A: take_glimpses, one cluster per row =====================
+    // position statistics are double-buffered: a fast cluster must not overwrite the value a
+    // slower cluster is still reading for THIS step's window
+    const float* rowpos_rd = a.rowpos + (size_t)(i & 1) * R;
+    float* rowpos_wr = a.rowpos + (size_t)((i + 1) & 1) * R;
+    if (cluster_id < R) {
+      const int row = cluster_id;
+      // window (lvsr/bricks/attention.py:123-163)
+      int b0, b1;
+      float lo = -1e30f, hi = 1e30f;
+      if (a.prior.type == LVSR_PRIOR_EXPANDING) {
+        const double st = (double)i;                     // step[0] == i under teacher forcing
+        double bb = a.prior.initial_begin + st * a.prior.min_speed;
+        double ee = a.prior.initial_end + st * a.prior.max_speed;
+        bb = fmax(0.0, fmin((double)(a.Tp - 1), bb));
+        ee = fmax(0.0, fmin((double)a.Tp, ee));
+        b0 = (int)floor(bb);
+        b1 = (int)ceil(ee);
+      } else {
+        float* wsh = att + att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs) - 8;   // spare floats at the tail
+        if (warp == 0) {
+          float mn = 1e30f, mx = -1e30f;
+          for (int r = lane; r < R; r += 32) {
+            const double pos = (double)__ldcg(rowpos_rd + r);
+            mn = fminf(mn, (float)floor(pos - a.prior.before));
+            mx = fmaxf(mx, (float)ceil(pos + a.prior.after));
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          }
+          if (lane == 0) { wsh[0] = mn; wsh[1] = mx; }
+        }
+        __syncthreads();
+        b0 = (int)fmaxf(0.f, wsh[0]);
+        b1 = (int)fminf((float)a.Tp, wsh[1]);
+        const double pos = (double)__ldcg(rowpos_rd + row);
+        lo = (float)floor(pos - a.prior.before);
+        hi = (float)ceil(pos + a.prior.after);
+        __syncthreads();
+      }
+      AttRowIO io;
+      io.P = a.P; io.H = a.H; io.maskH = a.maskH;
+      io.q_row = a.q + (long long)row * M;
+      io.w_prev = w_prev + (long long)row * a.Tp;
+      io.filt = a.filt; io.Wh = a.Wh; io.v = a.v; io.v_bias = a.v_bias;
+      io.w_out = w_cur + (long long)row * a.Tp;
+      io.e_out = e_cur + (long long)row * a.Tp;
+      io.ctx_out = ctx_cur + (long long)row * E;
+      io.u = row; io.U = R; io.Tp = a.Tp; io.M = M; io.E = E; io.K = a.K; io.n = a.n;
+      io.normalizer = a.normalizer;
+      io.b0 = b0; io.b1 = b1; io.lo = lo; io.hi = hi;
+      io.rowpos_out = (a.prior.type == LVSR_PRIOR_EXPANDING) ? nullptr : (rowpos_wr + row);
+      io.rowpos_mode = a.prior.type;
+      io.trace = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)i * 8 : nullptr;
+      attention_row(io, att, a.tc_cap, rank, cs, true, true, false);
+    }
+    DS_STAMP(1);
+    grid_sync(a.bar, G, gen);
+    DS_STAMP(2);
+
+    // ================= phase B1: gates + candidate inputs ==============================
+    if (in1) {
+      DenseIO d = {};
+      d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = R; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
+      d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.s = s_cur; d.z = a.z; d.hr = a.hr; d.ai = a.ai;
+      dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cg_ * a.nc1, red);
+    }
+    DS_STAMP(3);
+    grid_sync(a.bar, G, gen);
+    DS_STAMP(4);
+
+    // ================= phase B2: candidate, blend, label mask ===========================
+    if (in2) {
+      DenseIO d = {};
+      d.X1 = a.hr; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = R; d.N = C; d.mode = EP_CAND; d.C = C;
+      d.add = a.ai; d.arow = nullptr; d.s = s_cur; d.z = a.z;
+      d.rmask = a.lmask ? a.lmask + (size_t)i * R : nullptr;
+      d.out = s_next;
+      dense_dispatch(a.nc2 / 8, d, w2s, ws2, r0, cg_ * a.nc2, red);
+    }
+    DS_STAMP(5);
+    grid_sync(a.bar, G, gen);
+    DS_STAMP(6);
+
+    // ================= phase B3: query of the next step ================================
+    if (i + 1 < a.L) {
+      if (in3) {
+        DenseIO d = {};
+        d.X1 = s_next; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = R; d.N = M; d.mode = EP_QUERY; d.C = C;
+        d.out = a.q;
+        dense_dispatch(a.nc3 / 8, d, w3s, ws3, r0, cg_ * a.nc3, red);
+      }
+      DS_STAMP(7);
+      grid_sync(a.bar, G, gen);
+      DS_STAMP(8);
+    }
+  }
+  cluster.sync();   // no CTA exits while a peer may still address its shared memory
+}
+
+int g_sms = 0;
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+int round_up8(int x) { return (x + 7) & ~7; }
+bool kper_ok(int ktot) {
+  const int kp = ktot / 32;
+  return ktot % 128 == 0 && (kp == 4 || kp == 8 || kp == 12 || kp == 16 || kp == 24);
+}
+
+// Fill the derived fields for a grid of G CTAs; returns the dynamic shared memory in bytes (0 = unsupported).
+size_t derive(DecScanArgs& a, int cs, int G) {
+  const int R = a.B, C = a.C, E = a.E, M = a.M;
+  const int nrg = ceil_div(R, DS_ROWS);
+  const int ncg = G / nrg;
+  if (ncg < 1) return 0;
+  a.cs = cs;
+  a.tc_cap = ceil_div(a.Tp, cs);
+  a.nrg = nrg;
+  a.nc1 = round_up8(ceil_div(3 * C, ncg));
+  a.nc2 = round_up8(ceil_div(C, ncg));
+  a.nc3 = round_up8(ceil_div(M, ncg));
+  if (a.nc1 > 24 || a.nc2 > 24 || a.nc3 > 24) return 0;
+  size_t f = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
+  f = (f + 3) & ~(size_t)3;
+  f += (size_t)(E + C) * (a.nc1 + 4) + (size_t)C * (a.nc2 + 4) + (size_t)C * (a.nc3 + 4);
+  f = (f + 3) & ~(size_t)3;
+  f += (size_t)DS_WARPS * DS_ROWS * std::max(a.nc1, std::max(a.nc2, a.nc3));
+  const size_t bytes = f * sizeof(float) + 64;
+  return bytes <= 227 * 1024 ? bytes : 0;
+}
+
+int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
+  *supported = 0;
+  const int sms = sm_count();
+  const int R = a.B, C = a.C, E = a.E, M = a.M;
+  if (!kper_ok(E + C) || !kper_ok(C) || !(M == 128 || M == 256 || M == 512) || E % 4 != 0 || E / 4 > DS_THREADS) return 0;
+  if (a.K < 1 || a.K > 16 || R < 1) return 0;
+  int cs = 1;
+  while (cs < 8 && R * cs * 2 <= sms && ceil_div(a.Tp, cs * 2) >= 16) cs *= 2;
+  LVSR_CUDA_OK(cudaFuncSetAttribute(dec_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (; cs >= 1; cs >>= 1) {
+    int G = (sms / cs) * cs;
+    size_t smem = derive(a, cs, G);
+    if (smem == 0) continue;
+    // every cluster must be co-resident (grid barrier): ask the driver how many fit.  GPCs of
+    // 16-20 SMs hold only two 8-CTA clusters each, so large clusters cannot cover all SMs.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(DS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, dec_scan_kernel, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if (max_clusters * cs < G) {
+      G = max_clusters * cs;
+      if (G < cs) continue;
+      smem = derive(a, cs, G);
+      if (smem == 0) continue;
+      cfg.gridDim = dim3(G);
+      cfg.dynamicSmemBytes = smem;
+    }
+    if (R * cs > G) continue;        // not enough clusters for one per row: try a smaller cluster
+    LVSR_CUDA_OK(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      continue;                      // no non-cooperative fallback: a partial grid would deadlock
+    }
+    g_launch_count++;
+    *supported = 1;
+    return 0;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// Runs the persistent decoder if the shapes fit (*supported = 1); otherwise leaves everything
+// untouched (*supported = 0) and the caller falls back to the per-step kernels.
+int dec_scan_try(DecScanArgs& a, int* supported, cudaStream_t stream) {
+  ProfScope prof("dec_scan", stream);
+  return plan_and_launch(a, supported, stream);
+}
+
+}  // namespace lvsr

@@ -116,6 +116,35 @@ struct ReadoutArgs {
 };
 int readout_costs(const ReadoutArgs& a, cudaStream_t stream);
 
+// ---- dec_scan.cu: persistent teacher-forced decoder -----------------------------------
+struct DecScanArgs {
+  const float *P, *H, *maskH;          // [Tp,B,M], [Tp,B,E], [Tp,B]
+  const float *filt, *Wh, *v;          // attention constants
+  float v_bias;
+  PriorParams prior;
+  const float* Wb1;                    // [E+C, 3C]: rows <E = distribute [gates|inputs], rows >=E = [state_to_gates | 0]
+  const float* Wstate;                 // [C, C]
+  const float* Ws;                     // [C, M]
+  const float* FF;                     // [(V+1), 3C] fork(feedback(y)), gate columns first
+  const long long* labels;             // [L, B]
+  const float* lmask;                  // [L, B] or nullptr
+  float* s_all;                        // [(L+1), B, C]; s_all[0] = initial states on entry
+  float* ctx_all;                      // [L, B, E]
+  const float* w0;                     // [B, Tp] initial alignment
+  float* w_seq;                        // [L, B, Tp] or nullptr
+  float* w_pp[2];                      // ping-pong alignment buffers (used when w_seq == nullptr)
+  float* e_seq;                        // [L, B, Tp] or nullptr
+  float* e_scratch;                    // [B, Tp]
+  float *q, *z, *hr, *ai;              // [B,M], [B,C] x3
+  float* rowpos;                       // [2, B] (double-buffered per step), zero on entry
+  unsigned* bar;                       // [2] grid barrier words
+  unsigned long long* trace;           // optional [2 CTAs][L][9] globaltimer stamps (debug), or nullptr
+  int Tp, B, L, M, E, C, K, n, normalizer;
+  // derived by dec_scan_plan
+  int cs, tc_cap, nrg, nc1, nc2, nc3;
+};
+int dec_scan_try(DecScanArgs& a, int* supported, cudaStream_t stream);
+
 // small utility kernels
 int fill_f32(float* p, long long n, float v, cudaStream_t stream);
 int fill_i64(long long* p, long long n, long long v, cudaStream_t stream);

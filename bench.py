@@ -281,7 +281,7 @@ def main():
     step_device()
     torch.cuda.synchronize(dev)
     import ctypes as C
-    for cls in ("gemm", "bigru", "attention", "window", "dense", "readout"):
+    for cls in ("gemm", "bigru", "attention", "window", "dense", "dec_scan", "readout"):
         tot, cnt = C.c_double(), C.c_int64()
         lib.lvsr_profile_read(cls.encode(), C.byref(tot), C.byref(cnt))
         prof[cls] = {"ms": tot.value, "launches": cnt.value}
@@ -296,13 +296,20 @@ def main():
     e2e_value = frames / (ms_host / args.steps * 1e-3)
     peaks, peak_src = measured_peaks()
     Tp = rec.encoded_length(W["T"])
-    att = prof["attention"]
     step_bytes = attention_step_bytes(W["B"], Tp, NET["dim_matcher"], 2 * NET["dims_bidir"][-1])
-    att_us = att["ms"] * 1e3 / max(1, att["launches"])
-    achieved = step_bytes / (att_us * 1e-6) / 1e9 if att_us > 0 else 0.0
-    # the whole decoder step (attention + window + dense GRU pieces), the north-star's unit
-    dec_ms = prof["attention"]["ms"] + prof["window"]["ms"] + prof["dense"]["ms"]
-    dec_us = dec_ms * 1e3 / max(1, att["launches"])
+    if prof["dec_scan"]["launches"] > 0:
+        # persistent decoder: one launch runs all L attention+GRU steps
+        kern = "dec_scan_kernel (persistent attention+decoder scan, %d steps per launch)" % W["L"]
+        launch_bytes = step_bytes * W["L"]
+        k_us = prof["dec_scan"]["ms"] * 1e3 / prof["dec_scan"]["launches"]
+        dec_us = k_us / W["L"]
+    else:
+        att = prof["attention"]
+        kern = "att_step_kernel (attention step of the decoder)"
+        launch_bytes = step_bytes
+        k_us = att["ms"] * 1e3 / max(1, att["launches"])
+        dec_us = (prof["attention"]["ms"] + prof["window"]["ms"] + prof["dense"]["ms"]) * 1e3 / max(1, att["launches"])
+    achieved = launch_bytes / (k_us * 1e-6) / 1e9 if k_us > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -312,10 +319,10 @@ def main():
                 "d2h_bytes_per_step": int(W["L"] * W["B"] * 4)},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "att_step_kernel (attention step of the decoder)",
+        "roofline": {"bound": "hbm", "kernel": kern,
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": step_bytes, "us_per_launch": att_us,
+                     "algorithmic_bytes_per_launch": launch_bytes, "us_per_launch": k_us,
                      "decoder_step_us": dec_us,
                      "decoder_step_frac": (step_bytes / (dec_us * 1e-6) / 1e9 / peaks["hbm_gbs"]) if dec_us > 0 else 0.0,
                      "how": "CUDA events around every launch of the class in a separate profiled pass"},
