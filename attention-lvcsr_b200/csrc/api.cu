@@ -138,6 +138,10 @@ struct lvsr_model {
   float* Wff_cat = nullptr;         // [Cfb, 3C] = [fork gate_inputs | fork inputs]
   float* bff_cat = nullptr;         // [3C]
   float* FF = nullptr;              // [(V+1), 3C] = lookup . Wff_cat + bff_cat
+  // K-major tf32 hi/lo splits of the dense-projection weights (tcgen05 path); null = SIMT path
+  std::vector<float*> Wcat_hi, Wcat_lo;
+  float *Wp_hi = nullptr, *Wp_lo = nullptr;
+  bool use_tc = true;
   float v_bias = 0.f;               // host copy of energy_comp/linear.b
   bool finalized = false;
   Arena ws;
@@ -324,13 +328,14 @@ size_t encoder_ws_bytes(const lvsr_model* m, int T, int B) {
     const int D = m->cfg.dims_bidir[l], k = m->cfg.subsample[l];
     const int Tout = ceil_div(Tl, k);
     total += ((size_t)Tl * B * 6 * D + (size_t)Tout * B * 2 * D) * sizeof(float) + 1024;
+    total += (size_t)2 * Tl * B * (l == 0 ? m->cfg.num_features : 2 * m->cfg.dims_bidir[l - 1]) * sizeof(float) + 1024;
     Tl = Tout;
   }
   return total + (1 << 16);
 }
 size_t cost_ws_bytes(const lvsr_model* m, int Tp, int B, int L) {
   const lvsr_config& c = m->cfg;
-  size_t f = (size_t)Tp * B * c.dim_matcher + (size_t)(L + 1) * B * c.dim_dec + (size_t)L * B * m->E +
+  size_t f = (size_t)Tp * B * c.dim_matcher + (size_t)2 * Tp * B * m->E + (size_t)(L + 1) * B * c.dim_dec + (size_t)L * B * m->E +
              (size_t)4 * B * Tp + (size_t)L * B * c.post_merge_dim + (size_t)B * c.dim_matcher +
              (size_t)3 * B * c.dim_dec + 4 * B + 64;
   return f * sizeof(float) + (1 << 16);
@@ -424,6 +429,10 @@ int lvsr_model_destroy(lvsr_model* m) {
   for (auto& p : m->params) if (p.dev) cudaFree(p.dev);
   for (float* p : m->Wcat) if (p) cudaFree(p);
   for (float* p : m->bcat) if (p) cudaFree(p);
+  for (float* p : m->Wcat_hi) if (p) cudaFree(p);
+  for (float* p : m->Wcat_lo) if (p) cudaFree(p);
+  if (m->Wp_hi) cudaFree(m->Wp_hi);
+  if (m->Wp_lo) cudaFree(m->Wp_lo);
   if (m->Wd_cat) cudaFree(m->Wd_cat);
   if (m->Wb1) cudaFree(m->Wb1);
   if (m->Wff_cat) cudaFree(m->Wff_cat);
@@ -513,6 +522,38 @@ int lvsr_model_finalize(lvsr_model* m) {
   if (int rc = copy_cols(m->Wff_cat, 3 * C, 2 * C, m->P(g + "/fork/fork_inputs.W"), Cfb, C, st)) return rc;
   if (int rc = copy_cols(m->bff_cat, 3 * C, 0, m->P(g + "/fork/fork_gate_inputs.b"), 1, 2 * C, st)) return rc;
   if (int rc = copy_cols(m->bff_cat, 3 * C, 2 * C, m->P(g + "/fork/fork_inputs.b"), 1, C, st)) return rc;
+  // tensor-core operands: K-major tf32 hi/lo pairs of the fork and preprocess weights
+  m->use_tc = getenv("LVSR_NO_TC_GEMM") == nullptr;
+  if (m->use_tc) {
+    if (m->Wcat_hi.empty()) {
+      int dk = c.num_features;
+      for (int l = 0; l < c.num_layers; ++l) {
+        const int D = c.dims_bidir[l];
+        float *h = nullptr, *lo = nullptr;
+        if (gemm_tc_supported(128, 6 * D, dk)) {
+          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h), (size_t)dk * 6 * D * sizeof(float)));
+          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&lo), (size_t)dk * 6 * D * sizeof(float)));
+        }
+        m->Wcat_hi.push_back(h);
+        m->Wcat_lo.push_back(lo);
+        dk = 2 * D;
+      }
+      if (gemm_tc_supported(128, c.dim_matcher, m->E)) {
+        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_hi), (size_t)m->E * c.dim_matcher * sizeof(float)));
+        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_lo), (size_t)m->E * c.dim_matcher * sizeof(float)));
+      }
+    }
+    int dk = c.num_features;
+    for (int l = 0; l < c.num_layers; ++l) {
+      const int D = c.dims_bidir[l];
+      if (m->Wcat_hi[l])
+        if (int rc = split_weight_tf32(m->Wcat[l], dk, 6 * D, m->Wcat_hi[l], m->Wcat_lo[l], st)) return rc;
+      dk = 2 * D;
+    }
+    if (m->Wp_hi)
+      if (int rc = split_weight_tf32(m->P(std::string(ATT) + "/preprocess.W"), m->E, c.dim_matcher, m->Wp_hi, m->Wp_lo, st))
+        return rc;
+  }
   // fork(feedback(y)) for every symbol y, once: [(V+1), 3C]
   GemmArgs ff = make_gemm(m->P(g + "/readout/lookupfeedback/lookuptable.W"), V + 1, Cfb, m->Wff_cat, 3 * C,
                           m->bff_cat, m->FF);
@@ -551,8 +592,17 @@ int lvsr_encoder_forward(lvsr_model* m, const float* x, const float* mask, int32
     const int rows = Tl * B;
     float* pre = m->ws.f32((size_t)rows * 6 * D);
     LVSR_CHECK(pre, "out of device memory (encoder pre-activations)");
-    GemmArgs g = make_gemm(cur, rows, din, m->Wcat[l], 6 * D, m->bcat[l], pre);
-    if (int rc = gemm_bias(g, st)) return rc;
+    if (m->use_tc && l < (int)m->Wcat_hi.size() && m->Wcat_hi[l] && gemm_tc_supported(rows, 6 * D, din)) {
+      const size_t mark = m->ws.off;
+      float* a_hi = m->ws.f32((size_t)rows * din);
+      float* a_lo = m->ws.f32((size_t)rows * din);
+      LVSR_CHECK(a_hi && a_lo, "out of device memory (tf32 split scratch)");
+      if (int rc = gemm_tc(cur, a_hi, a_lo, rows, din, m->Wcat_hi[l], m->Wcat_lo[l], 6 * D, m->bcat[l], pre, 6 * D, st)) return rc;
+      if (m->ws.off <= m->ws.cap) m->ws.off = mark;     // scratch is dead once the GEMM is enqueued (stream order)
+    } else {
+      GemmArgs g = make_gemm(cur, rows, din, m->Wcat[l], 6 * D, m->bcat[l], pre);
+      if (int rc = gemm_bias(g, st)) return rc;
+    }
     const int Tout = ceil_div(Tl, k);
     float* out = (l == c.num_layers - 1) ? attended : m->ws.f32((size_t)Tout * B * 2 * D);
     LVSR_CHECK(out, "out of device memory (encoder layer output)");
@@ -577,6 +627,14 @@ int lvsr_preprocess(lvsr_model* m, const float* attended, int32_t Tp, int32_t U,
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && out && Tp > 0 && U > 0, "preprocess: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m->use_tc && m->Wp_hi && gemm_tc_supported(Tp * U, m->cfg.dim_matcher, m->E)) {
+    ArenaScope scope(m, st);
+    float* a_hi = m->ws.f32((size_t)Tp * U * m->E);
+    float* a_lo = m->ws.f32((size_t)Tp * U * m->E);
+    LVSR_CHECK(a_hi && a_lo, "out of device memory (tf32 split scratch)");
+    return gemm_tc(attended, a_hi, a_lo, Tp * U, m->E, m->Wp_hi, m->Wp_lo, m->cfg.dim_matcher,
+                   m->P(std::string(ATT) + "/preprocess.b"), out, m->cfg.dim_matcher, st);
+  }
   GemmArgs g = make_gemm(attended, Tp * U, m->E, m->P(std::string(ATT) + "/preprocess.W"), m->cfg.dim_matcher,
                          m->P(std::string(ATT) + "/preprocess.b"), out);
   return gemm_bias(g, st);

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include -I."
 OBJS=()
-for f in gemm bigru attention decoder dec_scan api; do
+for f in gemm gemm_tc bigru attention decoder dec_scan api; do
   if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ kernels.h -nt "$f.o" ] || [ common.cuh -nt "$f.o" ] || [ attention_row.cuh -nt "$f.o" ] || [ ../../include/lvsr_b200.h -nt "$f.o" ]; then
     echo "nvcc $f.cu"
     $NVCC $FLAGS "$@" -c "$f.cu" -o "$f.o"

@@ -28,6 +28,12 @@ inline GemmArgs make_gemm(const float* A, int M, int K, const float* W, int N, c
   return g;
 }
 
+// ---- gemm_tc.cu: tcgen05 / TMEM / TMA path (3xTF32 split) ------------------------------
+bool gemm_tc_supported(int M, int N, int K);
+int split_weight_tf32(const float* W, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
+int gemm_tc(const float* A, float* A_hi, float* A_lo, int M, int K, const float* Wt_hi, const float* Wt_lo, int N,
+            const float* bias, float* C, int ldc, cudaStream_t stream);
+
 // ---- bigru.cu -----------------------------------------------------------------------
 struct BiGruArgs {
   const float* pre;        // [T*B, 6D]: per direction [inputs D | update-gate D | reset-gate D], fwd then bwd
