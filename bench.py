@@ -115,6 +115,21 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def max_over_ranks(value, world, device=None, dist=None):
+    """Step time of a sharded job = the slowest rank's (barrier-bracketed) device time."""
+    if world == 1:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def shard_seed(rank, base=1234):
+    """Every rank draws its own utterance shard (weak scaling: the global batch is world x B)."""
+    return base + rank
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -208,7 +223,7 @@ def main():
     rec.set_parameter_values(init_values(rec.parameter_shapes()))
     lib = pkg._lib.load()
 
-    x, m, labels, lm = synthetic_batch(W["B"], W["T"], W["F"], W["L"], W["V"], seed=1234 + rank)
+    x, m, labels, lm = synthetic_batch(W["B"], W["T"], W["F"], W["L"], W["V"], seed=shard_seed(rank))
     xd, md = torch.as_tensor(x, device=dev), torch.as_tensor(m, device=dev)
     yd, ymd = torch.as_tensor(labels, device=dev), torch.as_tensor(lm, device=dev)
     xh, mh = torch.as_tensor(x).pin_memory(), torch.as_tensor(m).pin_memory()
@@ -242,13 +257,9 @@ def main():
             total_ms += a.elapsed_time(b)
         return total_ms
 
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        import torch.distributed as dist
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    dist_mod = None
+    if world > 1:
+        import torch.distributed as dist_mod
 
     for _ in range(args.warmup):
         step_device()
@@ -262,7 +273,7 @@ def main():
     ms_dev = timed(step_device, args.steps)
     barrier()
     launches = int(lib.lvsr_launch_count(1))
-    ms_dev = max_over_ranks(ms_dev)
+    ms_dev = max_over_ranks(ms_dev, world, dev, dist_mod)
 
     # end to end through the host-buffer C-ABI call (wall clock around a synchronising call)
     barrier()
@@ -270,7 +281,7 @@ def main():
     for _ in range(args.steps):
         step_host()
     torch.cuda.synchronize(dev)
-    ms_host = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ms_host = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev, dist_mod)
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
