@@ -186,3 +186,122 @@ def test_full_size_properties():
     # batch independence: utterance 5 alone gives the same costs as inside the batch
     sub = rec.cost(x[:, 5:6], m[:, 5:6], labels[:, 5:6], lm[:, 5:6])
     assert rel_err(sub[:, 0], r["costs"][:, 5].cpu().numpy()) < 1e-4
+
+
+# ---- BASELINE.json configs as parity cases -------------------------------------------------
+
+def _peaky(cfg, seed, gain=40.0, eos_bias=24.0):
+    params = O.init_params(cfg, seed=seed, scale=10.0)
+    params["/recognizer/generator/readout/post_merge/mlp/linear_0.W"] *= gain
+    params["/recognizer/generator/readout/post_merge/mlp/linear_0.b"][cfg["eos_label"]] = eos_bias
+    return params
+
+
+def test_config1_greedy_decode_identical_tokens():
+    """configs[0]: 8 utterances x 200 frames x 40 fbank, 1-layer BiGRU(128), greedy decode."""
+    _torch()
+    cfg = O.make_config(num_features=40, dims_bidir=[128], subsample=[1], dim_dec=128, conv_n=100,
+                        conv_num_filters=10, num_phonemes=32, post_merge_dims=[128], maxout_pieces=2,
+                        max_decoded_length_scale=8.0)
+    params = _peaky(cfg, 3, eos_bias=4.0)
+    x, m, _, _ = O.synthetic_batch(cfg, B=8, T=200, seed=1234)
+    rec = make_recognizer(cfg, params)
+    # batched greedy generate (argmax emission) through the state functions, all 8 utterances at once
+    att_o, attm_o = O.encoder(cfg, params, x, m)
+    ys_o, costs_o, _ = O.generate_greedy(cfg, params, att_o, attm_o, 25)
+    att, attm = rec.encode(x, m)
+    ctx = dict(attended=att, attended_mask=attm, preprocessed=rec.preprocess(att))
+    st = rec._initial_states(att.shape[0], 8)
+    ys = []
+    for _ in range(25):
+        lp = rec._logprobs(ctx, st).cpu().numpy()
+        y = lp.argmin(axis=1)
+        ys.append(y)
+        st = rec._next_states(ctx, st, y)
+    assert np.array_equal(np.stack(ys), ys_o)
+    # and beam_size = 1 search of single utterances
+    rec.init_beam_search(1)
+    for b in range(2):
+        n = int(m[:, b].sum())
+        try:
+            want = O.beam_search(cfg, params, x[:n, b], 1)
+        except O.CandidateNotFoundError:
+            import sys
+            err = sys.modules[type(rec._beam_search).__module__].CandidateNotFoundError
+            with pytest.raises(err):
+                rec.beam_search({"recordings": x[:n, b]})
+            continue
+        got = rec.beam_search({"recordings": x[:n, b]})
+        assert got[0] == want[0]
+
+
+def test_config3_wsj_beam10_identical_tokens():
+    """configs[2]: WSJ architecture, beam_size = 10, char-level output (short utterance so the
+    float64 oracle search finishes in seconds)."""
+    _torch()
+    cfg = O.make_config(max_decoded_length_scale=6.0, **WSJ)
+    params = _peaky(cfg, 5)
+    rng = np.random.RandomState(4)
+    x = rng.normal(size=(160, cfg["num_features"]))
+    want_out, want_costs = O.beam_search(cfg, params, x, 10, stop_on="optimistic_future_cost", char_discount=0.1)
+    rec = make_recognizer(cfg, params)
+    rec.init_beam_search(10)
+    got_out, got_costs = rec.beam_search({"recordings": x}, stop_on="optimistic_future_cost", char_discount=0.1)
+    assert got_out == want_out
+    # the x40 readout gain makes the logits ~25 in magnitude: 1e-4 relative on them is ~2.5e-3 absolute per token
+    assert np.allclose(got_costs, want_costs, rtol=1e-3, atol=5e-3)
+
+
+def test_config5_timit_long_utterance_properties():
+    """configs[4] per GPU: 16 utterances x 2000 frames, 3x BiGRU(256) without subsampling
+    (T' = 2000), 63 output symbols, window_around_median prior."""
+    torch = _torch()
+    cfg = O.make_config(num_features=40, dims_bidir=[256, 256, 256], subsample=[1, 1, 1], dim_dec=256,
+                        dim_matcher=512, conv_n=100, conv_num_filters=10, num_phonemes=63,
+                        post_merge_dims=[256], maxout_pieces=2,
+                        prior=dict(type="window_around_median", before=100, after=100))
+    params = O.init_params(cfg, seed=2, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=16, T=2000, seed=5, dtype=np.float32, label_div=32)
+    rec = make_recognizer(cfg, params)
+    att, attm = rec.encode(x, m)
+    assert tuple(att.shape) == (2000, 16, 512)
+    r = rec.cost_matrix(labels, lm, att, attm, return_all=True)
+    w = r["weights"]
+    assert bool(torch.isfinite(r["costs"]).all())
+    assert torch.allclose(w.sum(dim=2), torch.ones_like(w.sum(dim=2)), atol=1e-4)
+    assert int((w > 0).sum(dim=2).max()) <= 201                      # the median window: at most before+after+1 positions
+    # one short utterance of the same architecture against the oracle
+    xs, ms, ls, lms = O.synthetic_batch(cfg, B=2, T=96, seed=6)
+    want = O.recognizer_cost(cfg, params, xs, ms, ls, lms)
+    got = rec.cost(xs, ms, ls, lms)
+    assert rel_err(got, want) < TOL
+
+
+def test_persistent_decoder_equals_stepwise_kernels(monkeypatch):
+    _torch()
+    cfg = O.make_config(prior=dict(type="window_around_mean", before=9, after=9), **PYRAMID)
+    params = O.init_params(cfg, seed=8, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=9, T=80, seed=9)
+    rec = make_recognizer(cfg, params)
+    att, attm = rec.encode(x, m)
+    a = rec.cost_matrix(labels, lm, att, attm, return_all=True)
+    monkeypatch.setenv("LVSR_NO_DEC_SCAN", "1")
+    b = rec.cost_matrix(labels, lm, att, attm, return_all=True)
+    for k in ("costs", "weights", "energies", "states", "weighted_averages"):
+        assert rel_err(a[k].cpu().numpy(), b[k].cpu().numpy()) < 2e-5, k
+
+
+def test_tensor_core_gemm_equals_fp32_tiles(monkeypatch):
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=10, scale=10.0)
+    x, m, _, _ = O.synthetic_batch(cfg, B=10, T=90, seed=11)
+    rec_tc = make_recognizer(cfg, params)
+    a, _ = rec_tc.encode(x, m)
+    pa = rec_tc.preprocess(a)
+    monkeypatch.setenv("LVSR_NO_TC_GEMM", "1")
+    rec_simt = make_recognizer(cfg, params)        # the switch is read at finalize
+    b, _ = rec_simt.encode(x, m)
+    pb = rec_simt.preprocess(b)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    assert rel_err(pa.cpu().numpy(), pb.cpu().numpy()) < 1e-5
