@@ -693,8 +693,9 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     d.hr = ws.f32((size_t)B * C);
     d.ai = ws.f32((size_t)B * C);
     d.rowpos = ws.f32((size_t)2 * B);
-    d.bar = reinterpret_cast<unsigned*>(ws.i32(4));
-    LVSR_CHECK(d.q && d.z && d.hr && d.ai && d.rowpos && d.bar, "out of device memory (decoder scan workspace)");
+    d.flags_capacity = 1024;
+    d.flags = reinterpret_cast<unsigned*>(ws.i32((size_t)4 * d.flags_capacity));
+    LVSR_CHECK(d.q && d.z && d.hr && d.ai && d.rowpos && d.flags, "out of device memory (decoder scan workspace)");
     if (int rc = fill_f32(d.rowpos, 2 * B, 0.f, st)) return rc;
     const bool trace = getenv("LVSR_DEC_TRACE") != nullptr;
     if (trace) {

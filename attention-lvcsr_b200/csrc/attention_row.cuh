@@ -69,6 +69,11 @@ struct AttRowIO {
   float* rowpos_out = nullptr;
   int rowpos_mode = 0;
   unsigned long long* trace = nullptr;   // optional [8] globaltimer stamps (debug)
+  // optional split-phase dependency: the query is produced by other CTAs; wait for their
+  // counters only after the conv phase (which does not need it)
+  const unsigned* q_flags = nullptr;
+  int q_flags_n = 0;
+  unsigned q_flags_value = 0;
 };
 
 __device__ __forceinline__ unsigned long long att_global_ns() {
@@ -220,7 +225,6 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
 
   ATT_STAMP(0);
   // ---- stage the row's query, the slice of the previous alignment, zero the energies ----
-  for (int i = tid; i < M; i += NT) s.sq[i] = read_through_l2 ? __ldcg(a.q_row + i) : a.q_row[i];
   if (!constants_staged) att_stage_constants(s, a.v, a.Wh, a.filt, M, K, n);
   {
     const int len = nt + 2 * n + 8;
@@ -300,6 +304,8 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       }
     }
   }
+  if (a.q_flags != nullptr) flags_wait(a.q_flags, a.q_flags_n, a.q_flags_value);
+  for (int i = tid; i < M; i += NT) s.sq[i] = read_through_l2 ? __ldcg(a.q_row + i) : a.q_row[i];
   __syncthreads();
   ATT_STAMP(2);
 

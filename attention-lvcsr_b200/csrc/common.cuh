@@ -66,6 +66,35 @@ __device__ __forceinline__ float tanhf_acc(float x) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+// ---- point-to-point synchronisation between co-resident CTAs ----------------------------
+// A producer publishes a monotonically increasing counter with a release store after its CTA
+// barrier (release is cumulative over bar.sync, so every thread's prior global writes are
+// covered); a consumer's warp 0 polls the counters it depends on with acquire loads, then the
+// CTA barrier extends the ordering to all its threads.  Data itself is read with ld.global.cg.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_arrive(unsigned* flag, unsigned value) {
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_gpu(flag, value);
+}
+__device__ __forceinline__ void flags_wait(const unsigned* flags, int n, unsigned value) {
+  if (threadIdx.x < 32) {
+    for (int j = threadIdx.x; j < n; j += 32) {
+      unsigned spins = 0;
+      while (ld_acquire_gpu(flags + j) < value) {
+        if (++spins > (1u << 22)) __trap();     // a lost producer must fail the launch, not hang the GPU
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // Packed fp32 pair arithmetic (Blackwell FFMA2): d = a * b + c on both halves of a 64-bit register.
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;

@@ -24,49 +24,6 @@ constexpr int DS_THREADS = ATT_NT;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_ROWS = 16;          // rows per dense tile
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned atom_add_acqrel_u32(unsigned* p, unsigned v) {
-  unsigned old;
-  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;\n" : "=r"(old) : "l"(p), "r"(v) : "memory");
-  return old;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-
-// bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident (cooperative launch).
-// Split-phase: grid_arrive publishes this CTA's writes (acq_rel RMW by thread 0 after the CTA
-// barrier -- release is cumulative over the barrier), grid_wait acquires everybody else's.
-// Cross-CTA data is always read with ld.global.cg (L2), so no L1 invalidation is needed.
-__device__ __forceinline__ void grid_arrive(unsigned* bar, unsigned nblocks, unsigned gen) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atom_add_acqrel_u32(&bar[0], 1u);
-    if (prev == nblocks - 1) {
-      bar[0] = 0;
-      st_release_u32(&bar[1], gen + 1);
-    }
-  }
-}
-__device__ __forceinline__ void grid_wait(unsigned* bar, unsigned& gen) {
-  if (threadIdx.x == 0) {
-    unsigned spins = 0;
-    while (ld_acquire_u32(&bar[1]) == gen) {
-      if (++spins > (1u << 23)) __trap();   // never hang the GPU on a lost CTA
-    }
-  }
-  gen++;
-  __syncthreads();
-}
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks, unsigned& gen) {
-  grid_arrive(bar, nblocks, gen);
-  grid_wait(bar, gen);
-}
-
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
@@ -210,6 +167,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = a.B, C = a.C, E = a.E, M = a.M;
 
+  // ---- who synchronises with whom --------------------------------------------------------
+  // island mode: the batch is cut into islands of <= 16 rows; an island's CTAs (its rows'
+  // attention clusters) also own the island's dense tiles, so islands never wait for each other.
+  // global mode (small batches): one island made of every CTA, rows tiled over nrg row groups.
+  int isl_cta0 = 0, isl_n = G, r0 = 0, Rlim = R, cgi = 0;
+  if (a.nisl > 0) {
+    const int base = R / a.nisl, rem = R % a.nisl;
+    const int row = min(cluster_id, R - 1);
+    int k = 0, start = 0;
+    for (; k < a.nisl; ++k) {
+      const int cnt = base + (k < rem ? 1 : 0);
+      if (row < start + cnt) { isl_n = cnt * cs; break; }
+      start += cnt;
+    }
+    isl_cta0 = start * cs;
+    r0 = start;
+    Rlim = start + isl_n / cs;
+    cgi = bid - isl_cta0;
+  } else {
+    r0 = (bid % a.nrg) * DS_ROWS;
+    cgi = bid / a.nrg;
+  }
+  const bool in1 = cgi < a.ncg && cgi * a.nc1 < 3 * C, in2 = cgi < a.ncg && cgi * a.nc2 < C,
+             in3 = cgi < a.ncg && cgi * a.nc3 < M;
+  unsigned* fA = a.flags + 0 * (size_t)G;
+  unsigned* fB1 = a.flags + 1 * (size_t)G;
+  unsigned* fB2 = a.flags + 2 * (size_t)G;
+  unsigned* fB3 = a.flags + 3 * (size_t)G;
+
   // ---- shared memory: [attention region][w1][w2][w3][red] -----------------------------
   float* att = smem;
   size_t off = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
@@ -221,34 +207,31 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   off = (off + 3) & ~(size_t)3;
   float* red = smem + off;
 
-  // dense tile of this CTA
-  const int rg = bid % a.nrg, cg_ = bid / a.nrg;
-  const int r0 = rg * DS_ROWS;
-  const bool in1 = cg_ * a.nc1 < 3 * C, in2 = cg_ * a.nc2 < C, in3 = cg_ * a.nc3 < M;
-
   // ---- one-time staging: weight slices + attention constants -----------------------------
   for (int i = tid; i < (E + C) * a.nc1; i += DS_THREADS) {
-    const int k = i / a.nc1, c = i % a.nc1, col = cg_ * a.nc1 + c;
+    const int k = i / a.nc1, c = i % a.nc1, col = cgi * a.nc1 + c;
     w1s[(size_t)k * ws1 + c] = (in1 && col < 3 * C) ? a.Wb1[(long long)k * 3 * C + col] : 0.f;
   }
   for (int i = tid; i < C * a.nc2; i += DS_THREADS) {
-    const int k = i / a.nc2, c = i % a.nc2, col = cg_ * a.nc2 + c;
+    const int k = i / a.nc2, c = i % a.nc2, col = cgi * a.nc2 + c;
     w2s[(size_t)k * ws2 + c] = (in2 && col < C) ? a.Wstate[(long long)k * C + col] : 0.f;
   }
   for (int i = tid; i < C * a.nc3; i += DS_THREADS) {
-    const int k = i / a.nc3, c = i % a.nc3, col = cg_ * a.nc3 + c;
+    const int k = i / a.nc3, c = i % a.nc3, col = cgi * a.nc3 + c;
     w3s[(size_t)k * ws3 + c] = (in3 && col < M) ? a.Ws[(long long)k * M + col] : 0.f;
   }
   att_stage_constants(att_carve(att, M, E, a.K, a.n, a.tc_cap, cs), a.v, a.Wh, a.filt, M, a.K, a.n);
   __syncthreads();
 
-  unsigned gen = 0;
-  DenseIO dq = {};   // query for the first step: q = s_0 . W_state
-  dq.X1 = a.s_all; dq.K1 = C; dq.X2 = nullptr; dq.K2 = 0; dq.R = R; dq.N = M; dq.mode = EP_QUERY; dq.C = C;
-  dq.out = a.q;
-  if (in3) dense_dispatch(a.nc3 / 8, dq, w3s, ws3, r0, cg_ * a.nc3, red);
+  // query of the first step: q = s_0 . W_state; publishes B3 counter 1
+  if (in3) {
+    DenseIO dq = {};
+    dq.X1 = a.s_all; dq.K1 = C; dq.X2 = nullptr; dq.K2 = 0; dq.R = Rlim; dq.N = M; dq.mode = EP_QUERY; dq.C = C;
+    dq.out = a.q;
+    dense_dispatch(a.nc3 / 8, dq, w3s, ws3, r0, cgi * a.nc3, red);
+  }
   cluster.sync();     // every CTA of the cluster is resident before the first DSMEM write
-  grid_sync(a.bar, G, gen);
+  flag_arrive(fB3 + bid, 1u);
 
   const int trace_slot = (bid == 0) ? 0 : (bid == G - 1 ? 1 : -1);
 #define DS_STAMP(j)                                                                         \
@@ -258,6 +241,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   } while (0)
   for (int i = 0; i < a.L; ++i) {
     DS_STAMP(0);
+    const unsigned step1 = (unsigned)i + 1u;
     const float* w_prev = (i == 0) ? a.w0 : (a.w_seq ? a.w_seq + (size_t)(i - 1) * R * a.Tp : a.w_pp[(i - 1) & 1]);
     float* w_cur = a.w_seq ? a.w_seq + (size_t)i * R * a.Tp : a.w_pp[i & 1];
     float* e_cur = a.e_seq ? a.e_seq + (size_t)i * R * a.Tp : a.e_scratch;
@@ -284,6 +268,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
         b0 = (int)floor(bb);
         b1 = (int)ceil(ee);
       } else {
+        // the batch-global cut needs the position statistic of EVERY row of the previous step
+        if (i > 0) flags_wait(fA, R * cs, (unsigned)i);
         float* wsh = att + att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs) - 8;   // spare floats at the tail
         if (warp == 0) {
           float mn = 1e30f, mx = -1e30f;
@@ -321,46 +307,51 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       io.rowpos_out = (a.prior.type == LVSR_PRIOR_EXPANDING) ? nullptr : (rowpos_wr + row);
       io.rowpos_mode = a.prior.type;
       io.trace = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)i * 8 : nullptr;
+      // the query of this step comes from the island's B3 tiles: waited for AFTER the conv
+      io.q_flags = fB3 + isl_cta0; io.q_flags_n = isl_n; io.q_flags_value = step1;
       attention_row(io, att, a.tc_cap, rank, cs, true, true, false);
     }
     DS_STAMP(1);
-    grid_sync(a.bar, G, gen);
+    flag_arrive(fA + bid, step1);
+    flags_wait(fA + isl_cta0, isl_n, step1);
     DS_STAMP(2);
 
     // ================= phase B1: gates + candidate inputs ==============================
     if (in1) {
       DenseIO d = {};
-      d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = R; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
+      d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = Rlim; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
       d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.s = s_cur; d.z = a.z; d.hr = a.hr; d.ai = a.ai;
-      dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cg_ * a.nc1, red);
+      dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cgi * a.nc1, red);
     }
     DS_STAMP(3);
-    grid_sync(a.bar, G, gen);
+    flag_arrive(fB1 + bid, step1);
+    flags_wait(fB1 + isl_cta0, isl_n, step1);
     DS_STAMP(4);
 
     // ================= phase B2: candidate, blend, label mask ===========================
     if (in2) {
       DenseIO d = {};
-      d.X1 = a.hr; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = R; d.N = C; d.mode = EP_CAND; d.C = C;
+      d.X1 = a.hr; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = Rlim; d.N = C; d.mode = EP_CAND; d.C = C;
       d.add = a.ai; d.arow = nullptr; d.s = s_cur; d.z = a.z;
       d.rmask = a.lmask ? a.lmask + (size_t)i * R : nullptr;
       d.out = s_next;
-      dense_dispatch(a.nc2 / 8, d, w2s, ws2, r0, cg_ * a.nc2, red);
+      dense_dispatch(a.nc2 / 8, d, w2s, ws2, r0, cgi * a.nc2, red);
     }
     DS_STAMP(5);
-    grid_sync(a.bar, G, gen);
+    flag_arrive(fB2 + bid, step1);
+    flags_wait(fB2 + isl_cta0, isl_n, step1);
     DS_STAMP(6);
 
     // ================= phase B3: query of the next step ================================
     if (i + 1 < a.L) {
       if (in3) {
         DenseIO d = {};
-        d.X1 = s_next; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = R; d.N = M; d.mode = EP_QUERY; d.C = C;
+        d.X1 = s_next; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = Rlim; d.N = M; d.mode = EP_QUERY; d.C = C;
         d.out = a.q;
-        dense_dispatch(a.nc3 / 8, d, w3s, ws3, r0, cg_ * a.nc3, red);
+        dense_dispatch(a.nc3 / 8, d, w3s, ws3, r0, cgi * a.nc3, red);
       }
       DS_STAMP(7);
-      grid_sync(a.bar, G, gen);
+      flag_arrive(fB3 + bid, step1 + 1u);     // consumed by the next step's attention after its conv
       DS_STAMP(8);
     }
   }
@@ -385,17 +376,24 @@ bool kper_ok(int ktot) {
 }
 
 // Fill the derived fields for a grid of G CTAs; returns the dynamic shared memory in bytes (0 = unsupported).
-size_t derive(DecScanArgs& a, int cs, int G) {
+// want_islands: cut the batch into independent islands of <= 16 rows (grid = R*cs exactly).
+size_t derive(DecScanArgs& a, int cs, int G, bool want_islands) {
   const int R = a.B, C = a.C, E = a.E, M = a.M;
-  const int nrg = ceil_div(R, DS_ROWS);
-  const int ncg = G / nrg;
-  if (ncg < 1) return 0;
   a.cs = cs;
   a.tc_cap = ceil_div(a.Tp, cs);
-  a.nrg = nrg;
-  a.nc1 = round_up8(ceil_div(3 * C, ncg));
-  a.nc2 = round_up8(ceil_div(C, ncg));
-  a.nc3 = round_up8(ceil_div(M, ncg));
+  if (want_islands) {
+    a.nisl = ceil_div(R, DS_ROWS);
+    a.ncg = (R / a.nisl) * cs;           // the smallest island's CTA count
+    a.nrg = 1;
+  } else {
+    a.nisl = 0;
+    a.nrg = ceil_div(R, DS_ROWS);
+    a.ncg = G / a.nrg;
+  }
+  if (a.ncg < 1) return 0;
+  a.nc1 = round_up8(ceil_div(3 * C, a.ncg));
+  a.nc2 = round_up8(ceil_div(C, a.ncg));
+  a.nc3 = round_up8(ceil_div(M, a.ncg));
   if (a.nc1 > 24 || a.nc2 > 24 || a.nc3 > 24) return 0;
   size_t f = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
   f = (f + 3) & ~(size_t)3;
@@ -416,8 +414,15 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
   while (cs < 8 && R * cs * 2 <= sms && ceil_div(a.Tp, cs * 2) >= 16) cs *= 2;
   LVSR_CUDA_OK(cudaFuncSetAttribute(dec_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   for (; cs >= 1; cs >>= 1) {
-    int G = (sms / cs) * cs;
-    size_t smem = derive(a, cs, G);
+    // prefer islands (grid = one cluster per row); fall back to one global island on all SMs
+    bool islands = R >= DS_ROWS;
+    int G = islands ? R * cs : (sms / cs) * cs;
+    size_t smem = derive(a, cs, G, islands);
+    if (smem == 0 && islands) {
+      islands = false;
+      G = (sms / cs) * cs;
+      smem = derive(a, cs, G, false);
+    }
     if (smem == 0) continue;
     // every cluster must be co-resident (grid barrier): ask the driver how many fit.  GPCs of
     // 16-20 SMs hold only two 8-CTA clusters each, so large clusters cannot cover all SMs.
@@ -441,15 +446,17 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       continue;
     }
     if (max_clusters * cs < G) {
+      if (islands) continue;          // islands need exactly one cluster per row
       G = max_clusters * cs;
       if (G < cs) continue;
-      smem = derive(a, cs, G);
+      smem = derive(a, cs, G, false);
       if (smem == 0) continue;
       cfg.gridDim = dim3(G);
       cfg.dynamicSmemBytes = smem;
     }
     if (R * cs > G) continue;        // not enough clusters for one per row: try a smaller cluster
-    LVSR_CUDA_OK(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+    LVSR_CHECK(G <= a.flags_capacity, "dec_scan: flag buffer too small");
+    LVSR_CUDA_OK(cudaMemsetAsync(a.flags, 0, (size_t)4 * G * sizeof(unsigned), stream));
     cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
     if (e != cudaSuccess) {

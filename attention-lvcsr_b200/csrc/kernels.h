@@ -143,11 +143,13 @@ struct DecScanArgs {
   float* e_scratch;                    // [B, Tp]
   float *q, *z, *hr, *ai;              // [B,M], [B,C] x3
   float* rowpos;                       // [2, B] (double-buffered per step), zero on entry
-  unsigned* bar;                       // [2] grid barrier words
+  unsigned* flags;                     // [4, grid] per-CTA progress counters (A, B1, B2, B3), zero on entry
   unsigned long long* trace;           // optional [2 CTAs][L][9] globaltimer stamps (debug), or nullptr
   int Tp, B, L, M, E, C, K, n, normalizer;
   // derived by dec_scan_plan
   int cs, tc_cap, nrg, nc1, nc2, nc3;
+  int flags_capacity;                  // CTAs the flag buffer was sized for
+  int nisl, ncg;                       // nisl > 0: independent islands of <= 16 rows; ncg column groups per island
 };
 int dec_scan_try(DecScanArgs& a, int* supported, cudaStream_t stream);
 
