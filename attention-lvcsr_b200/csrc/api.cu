@@ -337,6 +337,7 @@ size_t cost_ws_bytes(const lvsr_model* m, int Tp, int B, int L) {
   const lvsr_config& c = m->cfg;
   size_t f = (size_t)Tp * B * c.dim_matcher + (size_t)2 * Tp * B * m->E + (size_t)(L + 1) * B * c.dim_dec + (size_t)L * B * m->E +
              (size_t)4 * B * Tp + (size_t)L * B * c.post_merge_dim + (size_t)B * c.dim_matcher +
+             (size_t)L * B * (Tp + c.dim_matcher + c.dim_dec + 1) +
              (size_t)3 * B * c.dim_dec + 4 * B + 64;
   return f * sizeof(float) + (1 << 16);
 }
@@ -657,11 +658,10 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
   float* s_all = ws.f32((size_t)(L + 1) * B * C);
   float* ctx_all = wavg_out ? wavg_out : ws.f32((size_t)L * B * E);
   float* w0 = ws.f32((size_t)B * Tp);
-  float* wpp[2] = {nullptr, nullptr};
-  if (!weights_out) { wpp[0] = ws.f32((size_t)B * Tp); wpp[1] = ws.f32((size_t)B * Tp); }
+  float* wpp[2] = {ws.f32((size_t)B * Tp), ws.f32((size_t)B * Tp)};   // step-wise fallback only
   float* e_scratch = energies_out ? nullptr : ws.f32((size_t)B * Tp);
   float* merged = ws.f32((size_t)L * B * c.post_merge_dim);
-  LVSR_CHECK(P && s_all && ctx_all && w0 && merged && (weights_out || (wpp[0] && wpp[1])) && (energies_out || e_scratch),
+  LVSR_CHECK(P && s_all && ctx_all && w0 && merged && wpp[0] && wpp[1] && (energies_out || e_scratch),
              "out of device memory (decoder workspace)");
 
   if (int rc = lvsr_preprocess(m, attended, Tp, B, P, stream)) return rc;          // hoisted: B/bricks/attention.py:733-738
@@ -684,19 +684,24 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     d.FF = m->FF;
     d.labels = lab; d.lmask = labels_mask;
     d.s_all = s_all; d.ctx_all = ctx_all; d.w0 = w0;
-    d.w_seq = weights_out; d.w_pp[0] = wpp[0]; d.w_pp[1] = wpp[1];
     d.e_seq = energies_out; d.e_scratch = e_scratch;
     d.Tp = Tp; d.B = B; d.L = L; d.M = M; d.E = E; d.C = C; d.K = c.conv_num_filters; d.n = c.conv_n;
     d.normalizer = c.energy_normalizer;
-    d.q = ws.f32((size_t)B * M);
-    d.z = ws.f32((size_t)B * C);
-    d.hr = ws.f32((size_t)B * C);
-    d.ai = ws.f32((size_t)B * C);
-    d.rowpos = ws.f32((size_t)2 * B);
-    d.flags_capacity = 1024;
-    d.flags = reinterpret_cast<unsigned*>(ws.i32((size_t)4 * d.flags_capacity));
-    LVSR_CHECK(d.q && d.z && d.hr && d.ai && d.rowpos && d.flags, "out of device memory (decoder scan workspace)");
-    if (int rc = fill_f32(d.rowpos, 2 * B, 0.f, st)) return rc;
+    // per-step hand-over buffers of the data-flow decoder; everything another CTA polls starts
+    // as the sentinel (0xFF bytes)
+    d.w_all = weights_out ? weights_out : ws.f32((size_t)L * B * Tp);
+    d.q_all = ws.f32((size_t)L * B * M);
+    d.hr_all = ws.f32((size_t)L * B * C);
+    d.rowpos_all = ws.f32((size_t)(L + 1) * B);
+    LVSR_CHECK(d.w_all && d.q_all && d.hr_all && d.rowpos_all,
+               "out of device memory (decoder scan workspace)");
+    LVSR_CUDA_OK(cudaMemsetAsync(d.w_all, 0xFF, (size_t)L * B * Tp * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(d.q_all, 0xFF, (size_t)L * B * M * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(d.hr_all, 0xFF, (size_t)L * B * C * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(d.rowpos_all + B, 0xFF, (size_t)L * B * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(d.rowpos_all, 0, (size_t)B * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(s_all + (size_t)B * C, 0xFF, (size_t)L * B * C * sizeof(float), st));
+    LVSR_CUDA_OK(cudaMemsetAsync(ctx_all, 0xFF, (size_t)L * B * E * sizeof(float), st));
     const bool trace = getenv("LVSR_DEC_TRACE") != nullptr;
     if (trace) {
       d.trace = reinterpret_cast<unsigned long long*>(ws.i64((size_t)2 * L * 9 + (size_t)L * 8));

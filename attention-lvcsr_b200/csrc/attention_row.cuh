@@ -69,11 +69,6 @@ struct AttRowIO {
   float* rowpos_out = nullptr;
   int rowpos_mode = 0;
   unsigned long long* trace = nullptr;   // optional [8] globaltimer stamps (debug)
-  // optional split-phase dependency: the query is produced by other CTAs; wait for their
-  // counters only after the conv phase (which does not need it)
-  const unsigned* q_flags = nullptr;
-  int q_flags_n = 0;
-  unsigned q_flags_value = 0;
 };
 
 __device__ __forceinline__ unsigned long long att_global_ns() {
@@ -206,10 +201,12 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
 }
 
 // ATT_NT threads.  `constants_staged`: a persistent caller already ran att_stage_constants.
-// `read_through_l2`: q / previous alignment were written by other CTAs in this launch.
+// `flow`: q and the previous alignment are produced by other CTAs of the same launch into
+// sentinel-initialised buffers (common.cuh, "the data is the flag"): they are read with polling
+// loads and the outputs other CTAs consume are written with gpu-scope stores.
 // `entry_wait_pending`: the caller issued barrier.cluster.arrive at kernel entry.
 __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, int tc_cap, int rank, int cs,
-                                              bool constants_staged, bool read_through_l2,
+                                              bool constants_staged, bool flow,
                                               bool entry_wait_pending) {
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -231,7 +228,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
     for (int i = tid; i < len; i += NT) {
       const int prel = t0 - n + i;            // window-relative position; zero padding is
       float val = 0.f;                        // relative to the CUT
-      if (prel >= 0 && prel < Tw) val = read_through_l2 ? __ldcg(a.w_prev + b0 + prel) : a.w_prev[b0 + prel];
+      if (prel >= 0 && prel < Tw) val = flow ? ld_flow_f32(a.w_prev + b0 + prel) : a.w_prev[b0 + prel];
       s.salpha[i] = val;
     }
     for (int i = tid; i < nt + 16; i += NT) s.se[i] = 0.f;
@@ -304,8 +301,8 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       }
     }
   }
-  if (a.q_flags != nullptr) flags_wait(a.q_flags, a.q_flags_n, a.q_flags_value);
-  for (int i = tid; i < M; i += NT) s.sq[i] = read_through_l2 ? __ldcg(a.q_row + i) : a.q_row[i];
+  // the query is consumed only now: in flow mode its producers ran concurrently with the conv
+  for (int i = tid; i < M; i += NT) s.sq[i] = flow ? ld_flow_f32(a.q_row + i) : a.q_row[i];
   __syncthreads();
   ATT_STAMP(2);
 
@@ -442,12 +439,16 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   const float inv = 1.f / norm;
 
   for (int t = tid; t < nt; t += NT) {
-    a.w_out[b0 + t0 + t] = s.su[t] * myscale * inv;
+    const float wv = s.su[t] * myscale * inv;
+    if (flow) st_flow_f32(a.w_out + b0 + t0 + t, wv); else a.w_out[b0 + t0 + t] = wv;
     a.e_out[b0 + t0 + t] = s.se[t];
   }
   // zero outside the window (paste into zeros, attention.py:177-181); ranks interleave the work
   for (int pidx = rank * NT + tid; pidx < Tp; pidx += cs * NT) {
-    if (pidx < b0 || pidx >= b0 + Tw) { a.w_out[pidx] = 0.f; a.e_out[pidx] = 0.f; }
+    if (pidx < b0 || pidx >= b0 + Tw) {
+      if (flow) st_flow_f32(a.w_out + pidx, 0.f); else a.w_out[pidx] = 0.f;
+      a.e_out[pidx] = 0.f;
+    }
   }
   if (rank == 0) {
     for (int e = tid; e < E; e += NT) {
@@ -457,7 +458,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
         if (a.normalizer == LVSR_NORM_SOFTMAX) sc = (xs[r * 4 + 1] > 0.f) ? __expf(xs[r * 4 + 0] - gmax) : 0.f;
         acc = fmaf(sc, xctx[(size_t)r * E + e], acc);
       }
-      a.ctx_out[e] = acc * inv;
+      if (flow) st_flow_f32(a.ctx_out + e, acc * inv); else a.ctx_out[e] = acc * inv;
     }
   }
 
@@ -472,7 +473,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       if (rank == 0 && lane == 0) {
         float pos = 0.f;
         for (int r = 0; r < cs; ++r) pos = fmaf(scale_of(r), xs[r * 4 + 3], pos);
-        *a.rowpos_out = pos * inv;
+        st_flow_f32(a.rowpos_out, pos * inv);
       }
     } else {
       // median: first index j with cumsum(alpha) >= 0.5 -> j - 1 (0 when j == 0 or no crossing)
@@ -506,9 +507,9 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
         for (int o = 16; o > 0; o >>= 1) cross = min(cross, __shfl_xor_sync(0xffffffffu, cross, o));
         if (cross == 0x7fffffff) cross = nt - 1;          // rounding at the chunk edge
         const int j = b0 + t0 + cross;
-        if (lane == 0) *a.rowpos_out = (j == 0) ? 0.f : (float)(j - 1);
+        if (lane == 0) st_flow_f32(a.rowpos_out, (j == 0) ? 0.f : (float)(j - 1));
       } else if (rank == 0 && lane == 0 && !(total >= 0.5f)) {
-        *a.rowpos_out = 0.f;
+        st_flow_f32(a.rowpos_out, 0.f);
       }
     }
   }

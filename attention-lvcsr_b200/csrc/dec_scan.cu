@@ -41,8 +41,9 @@ struct DenseIO {
   int C;
   const float* add;             // [*, N] addend
   const long long* arow;        // row index into add (or null: identity)
-  const float* s;               // [R, C] current state
-  float* z; float* hr; float* ai;
+  float* hr;                    // EP_GATES: reset-gated state [R, C], consumed by every candidate tile
+  float* loc;                   // smem [3][DS_ROWS][ncu]: update gate, candidate input, state of this tile's units
+  int ncu;                      // units per tile (EP_GATES / EP_CAND)
   const float* rmask;           // [R] or null
   float* out;                   // EP_CAND: next state [R, C]; EP_QUERY: q [R, N]
 };
@@ -72,7 +73,19 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
     for (int kb = 0; kb < KPER / 4; ++kb) {
       const int k = kbeg + kb * 4;
       const float* src = (k < d.K1) ? (d.X1 + (long long)row * d.K1 + k) : (d.X2 + (long long)row * d.K2 + (k - d.K1));
-      xv[i][kb] = __ldcg(reinterpret_cast<const float4*>(src));
+      xv[i][kb] = ld_relaxed_f4(src);     // all requests in flight before the first check
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = min(r0 + rq * 2 + i, d.R - 1);
+#pragma unroll
+    for (int kb = 0; kb < KPER / 4; ++kb) {
+      if (!flow_ready(xv[i][kb])) {
+        const int k = kbeg + kb * 4;
+        const float* src = (k < d.K1) ? (d.X1 + (long long)row * d.K1 + k) : (d.X2 + (long long)row * d.K2 + (k - d.K1));
+        xv[i][kb] = ld_flow_f4(src);
+      }
     }
   }
 #pragma unroll
@@ -104,39 +117,40 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       if (ks == 0) red[(size_t)warp * (DS_ROWS * NC) + (rq * 2 + i) * NC + cq * NCL + j] = v;
     }
   __syncthreads();
+  const int C = d.C;
   for (int o = tid; o < DS_ROWS * NC; o += DS_THREADS) {
     const int rl = o / NC, cl = o % NC;
-    const int r = r0 + rl, c = c0 + cl;
-    if (r >= d.R || c >= d.N) continue;
+    const int r = r0 + rl;
+    if (r >= d.R) continue;
     float v = 0.f;
 #pragma unroll
     for (int wq = 0; wq < DS_WARPS; ++wq) v += red[(size_t)wq * (DS_ROWS * NC) + o];
-    if (d.add) {
-      const long long ar = d.arow ? d.arow[r] : (long long)r;
-      v += d.arow ? __ldg(d.add + ar * d.N + c) : __ldcg(d.add + ar * d.N + c);
-    }
-    const int C = d.C;
     if (d.mode == EP_GATES) {
-      if (c < C) {
-        d.z[(long long)r * C + c] = fast_sigmoid(v);
-      } else if (c < 2 * C) {
-        const int uu = c - C;
-        d.hr[(long long)r * C + uu] = __ldcg(d.s + (long long)r * C + uu) * fast_sigmoid(v);
-      } else {
-        d.ai[(long long)r * C + (c - 2 * C)] = v;
-      }
+      // tile columns are [update | reset | candidate input] of the SAME ncu units (c0 = first unit)
+      const int ncu = d.ncu, gate = cl / ncu, ul = cl - gate * ncu, u = c0 + ul;
+      if (gate >= 3 || u >= C) continue;
+      v += __ldg(d.add + d.arow[r] * 3 * C + gate * C + u);
+      float* lz = d.loc, *lai = d.loc + DS_ROWS * ncu, *ls = d.loc + 2 * DS_ROWS * ncu;
+      if (gate == 0) lz[rl * ncu + ul] = fast_sigmoid(v);
+      else if (gate == 1) st_flow_f32(d.hr + (long long)r * C + u, ls[rl * ncu + ul] * fast_sigmoid(v));
+      else lai[rl * ncu + ul] = v;
     } else if (d.mode == EP_CAND) {
-      const float cand = fast_tanh(v);
-      const float zz = __ldcg(d.z + (long long)r * C + c);
-      const float sold = __ldcg(d.s + (long long)r * C + c);
+      const int ncu = d.ncu, u = c0 + cl;
+      if (cl >= ncu || u >= C) continue;
+      float* lz = d.loc, *lai = d.loc + DS_ROWS * ncu, *ls = d.loc + 2 * DS_ROWS * ncu;
+      const float cand = fast_tanh(v + lai[rl * ncu + cl]);
+      const float zz = lz[rl * ncu + cl];
+      const float sold = ls[rl * ncu + cl];
       float sn = cand * zz + sold * (1.f - zz);
       if (d.rmask) {
         const float m = d.rmask[r];
         sn = m * sn + (1.f - m) * sold;
       }
-      d.out[(long long)r * C + c] = sn;
+      ls[rl * ncu + cl] = sn;
+      st_flow_f32(d.out + (long long)r * C + u, sn);
     } else {
-      d.out[(long long)r * d.N + c] = v;
+      const int c = c0 + cl;
+      if (c < d.N) st_flow_f32(d.out + (long long)r * d.N + c, v);
     }
   }
   __syncthreads();
@@ -189,12 +203,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
     r0 = (bid % a.nrg) * DS_ROWS;
     cgi = bid / a.nrg;
   }
-  const bool in1 = cgi < a.ncg && cgi * a.nc1 < 3 * C, in2 = cgi < a.ncg && cgi * a.nc2 < C,
-             in3 = cgi < a.ncg && cgi * a.nc3 < M;
-  unsigned* fA = a.flags + 0 * (size_t)G;
-  unsigned* fB1 = a.flags + 1 * (size_t)G;
-  unsigned* fB2 = a.flags + 2 * (size_t)G;
-  unsigned* fB3 = a.flags + 3 * (size_t)G;
+  // a CTA's gate tile (B1) and candidate tile (B2) cover the same nc2 units of the same rows, so
+  // the update gate, the candidate input and the state itself never leave its shared memory
+  const bool in2 = cgi < a.ncg && cgi * a.nc2 < C, in1 = in2, in3 = cgi < a.ncg && cgi * a.nc3 < M;
 
   // ---- shared memory: [attention region][w1][w2][w3][red] -----------------------------
   float* att = smem;
@@ -204,13 +215,18 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   float* w1s = smem + off; off += (size_t)(E + C) * ws1;
   float* w2s = smem + off; off += (size_t)C * ws2;
   float* w3s = smem + off; off += (size_t)C * ws3;
+  float* loc = smem + off; off += (size_t)3 * DS_ROWS * a.nc2;
   off = (off + 3) & ~(size_t)3;
   float* red = smem + off;
 
   // ---- one-time staging: weight slices + attention constants -----------------------------
   for (int i = tid; i < (E + C) * a.nc1; i += DS_THREADS) {
-    const int k = i / a.nc1, c = i % a.nc1, col = cgi * a.nc1 + c;
-    w1s[(size_t)k * ws1 + c] = (in1 && col < 3 * C) ? a.Wb1[(long long)k * 3 * C + col] : 0.f;
+    const int k = i / a.nc1, c = i % a.nc1, gate = c / a.nc2, u = cgi * a.nc2 + c % a.nc2;
+    w1s[(size_t)k * ws1 + c] = (in1 && u < C) ? a.Wb1[(long long)k * 3 * C + gate * C + u] : 0.f;
+  }
+  for (int i = tid; i < DS_ROWS * a.nc2; i += DS_THREADS) {
+    const int rl = i / a.nc2, r = r0 + rl, u = cgi * a.nc2 + i % a.nc2;
+    loc[2 * DS_ROWS * a.nc2 + i] = (in2 && r < Rlim && u < C) ? a.s_all[(long long)r * C + u] : 0.f;
   }
   for (int i = tid; i < C * a.nc2; i += DS_THREADS) {
     const int k = i / a.nc2, c = i % a.nc2, col = cgi * a.nc2 + c;
@@ -223,15 +239,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   att_stage_constants(att_carve(att, M, E, a.K, a.n, a.tc_cap, cs), a.v, a.Wh, a.filt, M, a.K, a.n);
   __syncthreads();
 
-  // query of the first step: q = s_0 . W_state; publishes B3 counter 1
+  // query of the first step: q = s_0 . W_state
   if (in3) {
     DenseIO dq = {};
     dq.X1 = a.s_all; dq.K1 = C; dq.X2 = nullptr; dq.K2 = 0; dq.R = Rlim; dq.N = M; dq.mode = EP_QUERY; dq.C = C;
-    dq.out = a.q;
+    dq.out = a.q_all;
     dense_dispatch(a.nc3 / 8, dq, w3s, ws3, r0, cgi * a.nc3, red);
   }
   cluster.sync();     // every CTA of the cluster is resident before the first DSMEM write
-  flag_arrive(fB3 + bid, 1u);
 
   const int trace_slot = (bid == 0) ? 0 : (bid == G - 1 ? 1 : -1);
 #define DS_STAMP(j)                                                                         \
@@ -241,19 +256,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   } while (0)
   for (int i = 0; i < a.L; ++i) {
     DS_STAMP(0);
-    const unsigned step1 = (unsigned)i + 1u;
-    const float* w_prev = (i == 0) ? a.w0 : (a.w_seq ? a.w_seq + (size_t)(i - 1) * R * a.Tp : a.w_pp[(i - 1) & 1]);
-    float* w_cur = a.w_seq ? a.w_seq + (size_t)i * R * a.Tp : a.w_pp[i & 1];
+    // No barriers or flags below: every cross-CTA value lives in a per-step, sentinel-filled
+    // buffer and is polled by its consumers (common.cuh).  Phases of different rows / tiles
+    // overlap freely; the only ordering is true data dependence.
+    const float* w_prev = (i == 0) ? a.w0 : a.w_all + (size_t)(i - 1) * R * a.Tp;
+    float* w_cur = a.w_all + (size_t)i * R * a.Tp;
     float* e_cur = a.e_seq ? a.e_seq + (size_t)i * R * a.Tp : a.e_scratch;
+    float* hr_cur = a.hr_all + (size_t)i * R * C;
     float* ctx_cur = a.ctx_all + (size_t)i * R * E;
     const float* s_cur = a.s_all + (size_t)i * R * C;
     float* s_next = a.s_all + (size_t)(i + 1) * R * C;
 
     // ================= phase A: take_glimpses, one cluster per row =====================
-    // position statistics are double-buffered: a fast cluster must not overwrite the value a
-    // slower cluster is still reading for THIS step's window
-    const float* rowpos_rd = a.rowpos + (size_t)(i & 1) * R;
-    float* rowpos_wr = a.rowpos + (size_t)((i + 1) & 1) * R;
+    const float* rowpos_rd = a.rowpos_all + (size_t)i * R;
+    float* rowpos_wr = a.rowpos_all + (size_t)(i + 1) * R;
     if (cluster_id < R) {
       const int row = cluster_id;
       // window (lvsr/bricks/attention.py:123-163)
@@ -269,12 +285,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
         b1 = (int)ceil(ee);
       } else {
         // the batch-global cut needs the position statistic of EVERY row of the previous step
-        if (i > 0) flags_wait(fA, R * cs, (unsigned)i);
         float* wsh = att + att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs) - 8;   // spare floats at the tail
         if (warp == 0) {
           float mn = 1e30f, mx = -1e30f;
           for (int r = lane; r < R; r += 32) {
-            const double pos = (double)__ldcg(rowpos_rd + r);
+            const double pos = (double)ld_flow_f32(rowpos_rd + r);
             mn = fminf(mn, (float)floor(pos - a.prior.before));
             mx = fmaxf(mx, (float)ceil(pos + a.prior.after));
           }
@@ -288,14 +303,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
         __syncthreads();
         b0 = (int)fmaxf(0.f, wsh[0]);
         b1 = (int)fminf((float)a.Tp, wsh[1]);
-        const double pos = (double)__ldcg(rowpos_rd + row);
+        const double pos = (double)ld_flow_f32(rowpos_rd + row);
         lo = (float)floor(pos - a.prior.before);
         hi = (float)ceil(pos + a.prior.after);
         __syncthreads();
       }
       AttRowIO io;
       io.P = a.P; io.H = a.H; io.maskH = a.maskH;
-      io.q_row = a.q + (long long)row * M;
+      io.q_row = a.q_all + ((size_t)i * R + row) * M;
       io.w_prev = w_prev + (long long)row * a.Tp;
       io.filt = a.filt; io.Wh = a.Wh; io.v = a.v; io.v_bias = a.v_bias;
       io.w_out = w_cur + (long long)row * a.Tp;
@@ -307,39 +322,31 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       io.rowpos_out = (a.prior.type == LVSR_PRIOR_EXPANDING) ? nullptr : (rowpos_wr + row);
       io.rowpos_mode = a.prior.type;
       io.trace = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)i * 8 : nullptr;
-      // the query of this step comes from the island's B3 tiles: waited for AFTER the conv
-      io.q_flags = fB3 + isl_cta0; io.q_flags_n = isl_n; io.q_flags_value = step1;
       attention_row(io, att, a.tc_cap, rank, cs, true, true, false);
     }
     DS_STAMP(1);
-    flag_arrive(fA + bid, step1);
-    flags_wait(fA + isl_cta0, isl_n, step1);
     DS_STAMP(2);
 
     // ================= phase B1: gates + candidate inputs ==============================
     if (in1) {
       DenseIO d = {};
       d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = Rlim; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
-      d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.s = s_cur; d.z = a.z; d.hr = a.hr; d.ai = a.ai;
-      dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cgi * a.nc1, red);
+      d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.hr = hr_cur; d.loc = loc; d.ncu = a.nc2;
+      dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cgi * a.nc2, red);
     }
     DS_STAMP(3);
-    flag_arrive(fB1 + bid, step1);
-    flags_wait(fB1 + isl_cta0, isl_n, step1);
     DS_STAMP(4);
 
     // ================= phase B2: candidate, blend, label mask ===========================
     if (in2) {
       DenseIO d = {};
-      d.X1 = a.hr; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = Rlim; d.N = C; d.mode = EP_CAND; d.C = C;
-      d.add = a.ai; d.arow = nullptr; d.s = s_cur; d.z = a.z;
+      d.X1 = hr_cur; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = Rlim; d.N = C; d.mode = EP_CAND; d.C = C;
+      d.loc = loc; d.ncu = a.nc2;
       d.rmask = a.lmask ? a.lmask + (size_t)i * R : nullptr;
       d.out = s_next;
       dense_dispatch(a.nc2 / 8, d, w2s, ws2, r0, cgi * a.nc2, red);
     }
     DS_STAMP(5);
-    flag_arrive(fB2 + bid, step1);
-    flags_wait(fB2 + isl_cta0, isl_n, step1);
     DS_STAMP(6);
 
     // ================= phase B3: query of the next step ================================
@@ -347,11 +354,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       if (in3) {
         DenseIO d = {};
         d.X1 = s_next; d.K1 = C; d.X2 = nullptr; d.K2 = 0; d.R = Rlim; d.N = M; d.mode = EP_QUERY; d.C = C;
-        d.out = a.q;
+        d.out = a.q_all + (size_t)(i + 1) * R * M;
         dense_dispatch(a.nc3 / 8, d, w3s, ws3, r0, cgi * a.nc3, red);
       }
       DS_STAMP(7);
-      flag_arrive(fB3 + bid, step1 + 1u);     // consumed by the next step's attention after its conv
       DS_STAMP(8);
     }
   }
@@ -391,14 +397,15 @@ size_t derive(DecScanArgs& a, int cs, int G, bool want_islands) {
     a.ncg = G / a.nrg;
   }
   if (a.ncg < 1) return 0;
-  a.nc1 = round_up8(ceil_div(3 * C, a.ncg));
   a.nc2 = round_up8(ceil_div(C, a.ncg));
+  a.nc1 = 3 * a.nc2;
   a.nc3 = round_up8(ceil_div(M, a.ncg));
   if (a.nc1 > 24 || a.nc2 > 24 || a.nc3 > 24) return 0;
   size_t f = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
   f = (f + 3) & ~(size_t)3;
   f += (size_t)(E + C) * (a.nc1 + 4) + (size_t)C * (a.nc2 + 4) + (size_t)C * (a.nc3 + 4);
   f = (f + 3) & ~(size_t)3;
+  f += (size_t)3 * DS_ROWS * a.nc2 + 4;
   f += (size_t)DS_WARPS * DS_ROWS * std::max(a.nc1, std::max(a.nc2, a.nc3));
   const size_t bytes = f * sizeof(float) + 64;
   return bytes <= 227 * 1024 ? bytes : 0;
@@ -455,9 +462,12 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       cfg.dynamicSmemBytes = smem;
     }
     if (R * cs > G) continue;        // not enough clusters for one per row: try a smaller cluster
-    LVSR_CHECK(G <= a.flags_capacity, "dec_scan: flag buffer too small");
-    LVSR_CUDA_OK(cudaMemsetAsync(a.flags, 0, (size_t)4 * G * sizeof(unsigned), stream));
     cfg.numAttrs = 2;
+    {
+      const char* bo = getenv("LVSR_FLOW_BACKOFF_NS");
+      const unsigned ns = bo ? (unsigned)atoi(bo) : 0u;
+      LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_backoff_ns, &ns, sizeof(ns), 0, cudaMemcpyHostToDevice, stream));
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
     if (e != cudaSuccess) {
       cudaGetLastError();

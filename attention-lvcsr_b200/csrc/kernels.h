@@ -134,22 +134,22 @@ struct DecScanArgs {
   const float* FF;                     // [(V+1), 3C] fork(feedback(y)), gate columns first
   const long long* labels;             // [L, B]
   const float* lmask;                  // [L, B] or nullptr
+  // Every buffer another CTA reads is per-step and pre-filled with the sentinel (0xFF bytes) by
+  // the host, except step 0 (s_all[0], rowpos_all[0], w0): written once, polled by consumers.
   float* s_all;                        // [(L+1), B, C]; s_all[0] = initial states on entry
   float* ctx_all;                      // [L, B, E]
   const float* w0;                     // [B, Tp] initial alignment
-  float* w_seq;                        // [L, B, Tp] or nullptr
-  float* w_pp[2];                      // ping-pong alignment buffers (used when w_seq == nullptr)
+  float* w_all;                        // [L, B, Tp] alignments (the caller's weights output or scratch)
   float* e_seq;                        // [L, B, Tp] or nullptr
   float* e_scratch;                    // [B, Tp]
-  float *q, *z, *hr, *ai;              // [B,M], [B,C] x3
-  float* rowpos;                       // [2, B] (double-buffered per step), zero on entry
-  unsigned* flags;                     // [4, grid] per-CTA progress counters (A, B1, B2, B3), zero on entry
-  unsigned long long* trace;           // optional [2 CTAs][L][9] globaltimer stamps (debug), or nullptr
+  float* q_all;                        // [L, B, M]
+  float* hr_all;                       // [L, B, C] reset-gated states (the only gate value that crosses CTAs)
+  float* rowpos_all;                   // [L+1, B]; rowpos_all[0] = 0
+  unsigned long long* trace;           // optional debug stamps, or nullptr
   int Tp, B, L, M, E, C, K, n, normalizer;
-  // derived by dec_scan_plan
+  // derived by the planner
   int cs, tc_cap, nrg, nc1, nc2, nc3;
-  int flags_capacity;                  // CTAs the flag buffer was sized for
-  int nisl, ncg;                       // nisl > 0: independent islands of <= 16 rows; ncg column groups per island
+  int nisl, ncg;                       // nisl > 0: islands of <= 16 rows whose CTAs own their dense tiles
 };
 int dec_scan_try(DecScanArgs& a, int* supported, cudaStream_t stream);
 
