@@ -66,6 +66,7 @@ __device__ __forceinline__ float tanhf_acc(float x) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+
 // ---- point-to-point synchronisation between co-resident CTAs ----------------------------
 // A producer publishes a monotonically increasing counter with a release store after its CTA
 // barrier (release is cumulative over bar.sync, so every thread's prior global writes are
@@ -103,6 +104,7 @@ __device__ __forceinline__ void flags_wait(const unsigned* flags, int n, unsigne
 constexpr unsigned LVSR_SENTINEL = 0xFFFFFFFFu;
 constexpr unsigned LVSR_SPIN_LIMIT = 1u << 22;
 static __constant__ unsigned g_flow_backoff_ns = 0;   // per translation unit; set by the launcher
+static __constant__ unsigned g_flow_spin_limit = LVSR_SPIN_LIMIT;
 __device__ __forceinline__ void st_flow_f32(float* p, float v) {
   asm volatile("st.relaxed.gpu.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
 }
@@ -111,7 +113,7 @@ __device__ __forceinline__ float ld_flow_f32(const float* p) {
   while (true) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     if (v != LVSR_SENTINEL) break;
-    if (++spins > LVSR_SPIN_LIMIT) __trap();     // a value that never arrives must fail the launch, not hang
+    if (++spins > g_flow_spin_limit) __trap();     // a value that never arrives must fail the launch, not hang
     if (g_flow_backoff_ns) __nanosleep(g_flow_backoff_ns);
   }
   return __uint_as_float(v);
@@ -138,7 +140,7 @@ __device__ __forceinline__ float4 ld_flow_f4(const float* p) {
                  : "l"(p)
                  : "memory");
     if (x != LVSR_SENTINEL && y != LVSR_SENTINEL && z != LVSR_SENTINEL && w != LVSR_SENTINEL) break;
-    if (++spins > LVSR_SPIN_LIMIT) __trap();
+    if (++spins > g_flow_spin_limit) __trap();
     if (g_flow_backoff_ns) __nanosleep(g_flow_backoff_ns);
   }
   return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));

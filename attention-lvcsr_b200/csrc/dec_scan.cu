@@ -467,6 +467,10 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       const char* bo = getenv("LVSR_FLOW_BACKOFF_NS");
       const unsigned ns = bo ? (unsigned)atoi(bo) : 0u;
       LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_backoff_ns, &ns, sizeof(ns), 0, cudaMemcpyHostToDevice, stream));
+      // profilers slow the kernel down by orders of magnitude: let them raise the hang guard
+      const char* sl = getenv("LVSR_FLOW_SPIN_LIMIT");
+      const unsigned lim = sl ? (unsigned)strtoul(sl, nullptr, 10) : LVSR_SPIN_LIMIT;
+      LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_spin_limit, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, stream));
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
     if (e != cudaSuccess) {

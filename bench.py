@@ -178,13 +178,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=WORKLOAD["B"],
+                    help="diagnostic only: utterances per GPU (the metric is quoted on the default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    W = WORKLOAD
+    W = dict(WORKLOAD, B=args.batch)
     config = {"workload": "configs[metric]: WSJ-shaped synthetic, batch %d x %d frames x %d fbank per GPU, "
                           "4-layer pyramidal BiGRU(256) + content+location attention + GRU(256) decoder, "
                           "%d teacher-forced steps" % (W["B"], W["T"], W["F"], W["L"]),
