@@ -95,4 +95,4 @@ def load():
 def check(rc):
     if rc != 0:
         msg = load().lvsr_last_error()
-        raise RuntimeError("lvsr_b200: " + (msg.decode() if msg else "error %d" % rc))
+        raise RuntimeError("lvsr_b200: " + (msg.decode("utf-8", "replace") if msg else "error %d" % rc))

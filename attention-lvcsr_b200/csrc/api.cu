@@ -415,8 +415,9 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
   for (auto& p : m->params) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p.dev), (size_t)p.count * sizeof(float));
     if (e != cudaSuccess) {
+      const std::string name = p.name;       // `p` dies with the model
       lvsr_model_destroy(m);
-      return set_error("cudaMalloc(%s) failed: %s", p.name.c_str(), cudaGetErrorString(e));
+      return set_error("cudaMalloc(%s) failed: %s", name.c_str(), cudaGetErrorString(e));
     }
     cudaMemset(p.dev, 0, (size_t)p.count * sizeof(float));
   }

@@ -65,6 +65,22 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < NCL; ++j) acc[i][j] = 0.f;
+  // Operand of this thread's epilogue (the tile has at most one output per thread): the label's
+  // row of the feedback table / the label mask.  Requested first -- two dependent global loads
+  // that would otherwise sit at the very end of the phase, on the decoder's critical path.
+  static_assert(DS_ROWS * NC <= DS_THREADS, "one output per thread");
+  float ep_pref = 0.f;
+  {
+    const int rl = tid / NC, cl = tid % NC, r = r0 + rl;
+    if (tid < DS_ROWS * NC && r < d.R) {
+      if (d.mode == EP_GATES) {
+        const int ncu = d.ncu, gate = cl / ncu, u = c0 + (cl - gate * ncu);
+        if (gate < 3 && u < d.C) ep_pref = __ldg(d.add + d.arow[r] * 3 * d.C + gate * d.C + u);
+      } else if (d.mode == EP_CAND) {
+        ep_pref = d.rmask ? __ldg(d.rmask + r) : 1.f;
+      }
+    }
+  }
   float4 xv[2][KPER / 4];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -118,7 +134,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
     }
   __syncthreads();
   const int C = d.C;
-  for (int o = tid; o < DS_ROWS * NC; o += DS_THREADS) {
+  for (int o = tid; o < DS_ROWS * NC; o += DS_THREADS) {     // at most one iteration
     const int rl = o / NC, cl = o % NC;
     const int r = r0 + rl;
     if (r >= d.R) continue;
@@ -129,7 +145,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       // tile columns are [update | reset | candidate input] of the SAME ncu units (c0 = first unit)
       const int ncu = d.ncu, gate = cl / ncu, ul = cl - gate * ncu, u = c0 + ul;
       if (gate >= 3 || u >= C) continue;
-      v += __ldg(d.add + d.arow[r] * 3 * C + gate * C + u);
+      v += ep_pref;
       float* lz = d.loc, *lai = d.loc + DS_ROWS * ncu, *ls = d.loc + 2 * DS_ROWS * ncu;
       if (gate == 0) lz[rl * ncu + ul] = fast_sigmoid(v);
       else if (gate == 1) st_flow_f32(d.hr + (long long)r * C + u, ls[rl * ncu + ul] * fast_sigmoid(v));
@@ -142,10 +158,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       const float zz = lz[rl * ncu + cl];
       const float sold = ls[rl * ncu + cl];
       float sn = cand * zz + sold * (1.f - zz);
-      if (d.rmask) {
-        const float m = d.rmask[r];
-        sn = m * sn + (1.f - m) * sold;
-      }
+      sn = ep_pref * sn + (1.f - ep_pref) * sold;     // label mask (1 when there is none)
       ls[rl * ncu + cl] = sn;
       st_flow_f32(d.out + (long long)r * C + u, sn);
     } else {
