@@ -81,33 +81,51 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // D: hidden units per direction; CS: CTAs per cluster.
+//
+// Work split inside a warp (the kernel is bound by instruction issue, see profiles/r1f_summary.md,
+// so the layout minimises instructions that are not FFMAs): lane = kg * CG + cg.
+//   kg (KL = 8 groups)  owns the k range [kg * D/8, +D/8) of both products -- exactly the slice of
+//                       h that one or half a peer CTA delivers, 128 contiguous bytes per row;
+//   cg (CG = 4 groups)  owns NC1/4 of the warp's gate columns and NC2/4 of its candidate columns.
+// A lane therefore accumulates RB x 2 gate sums and RB x 1 candidate sums over its D/8 k values and
+// the cross-lane reduction runs over the 8 kg-lanes only: 7 + 4 exchanges per step instead of
+// 31 + 15 over all 32 lanes.
 template <int D, int CS>
 __global__ void __launch_bounds__(NWARP * 32, 2)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
-  constexpr int KPL = D / 32;         // k values per lane
-  constexpr int KG = KPL / 4;         // float4 groups per lane; group q covers k = q*128 + 4*lane .. +3
+  constexpr int KL = 8;               // lanes that split k
+  constexpr int CG = 32 / KL;         // lanes that split the warp's columns
+  constexpr int KPG = D / KL;         // k values per lane
+  constexpr int KQ = KPG / 4;         // float4 groups per lane
   constexpr int NC2 = UC / NWARP;     // units per warp (candidate columns)
   constexpr int NC1 = 2 * NC2;        // gate columns per warp: [z units | r units]
-  static_assert(D % (CS * NWARP) == 0 && D % 128 == 0, "unsupported D / cluster size");
-  static_assert(128 % UC == 0 && UC % 4 == 0, "a lane's float4 group must sit inside one peer slice");
-  constexpr int N1 = RB * NC1, N2 = RB * NC2;
+  constexpr int CPL1 = NC1 / CG;      // gate columns per lane
+  constexpr int CPL2 = NC2 / CG;      // candidate columns per lane
+  static_assert(D % (CS * NWARP) == 0 && D % (4 * KL) == 0, "unsupported D / cluster size");
+  static_assert(NC2 % CG == 0 && CPL2 == 1, "one candidate column per lane");
+  static_assert(UC % KPG == 0 || KPG % UC == 0, "a lane's k range must not straddle peer slices unevenly");
+  static_assert(KPG <= UC, "a lane's k range sits inside one peer slice");
+  constexpr int N1 = RB * CPL1, N2 = RB * CPL2;        // per-lane partial sums of the two phases
   constexpr uint32_t SLICE_BYTES = RB * UC * sizeof(float);
   constexpr uint32_t FULL_BYTES = RB * D * sizeof(float);
 
-  // peer-major: slot p holds the [RB][UC] slice owned by CTA p -> one bulk copy per peer
-  __shared__ __align__(128) float hbuf[CS][RB][UC];     // h, all units
-  __shared__ __align__(128) float hrbuf[CS][RB][UC];    // h * reset, all units
+  // peer-major: slot p holds the [RB][UC] slice owned by CTA p -> one bulk copy per peer.  Slots
+  // are padded by 16 bytes: the 8 kg lanes of a warp read 8 different slots at the same offset,
+  // which without the pad is an 8-way bank conflict on every load (measured: 2x the step time).
+  constexpr int SLOT = RB * UC + 4;
+  __shared__ __align__(128) float hbuf[CS][SLOT];       // h, all units
+  __shared__ __align__(128) float hrbuf[CS][SLOT];      // h * reset, all units
   __shared__ __align__(128) float stage_h[RB][UC];      // own slice of h (source of the copies)
   __shared__ __align__(128) float stage_hr[RB][UC];     // own slice of h * reset
   __shared__ float zbuf[RB][UC];                        // update gates of the owned units
-  // state_to_state slice: [warp][kk][lane][c] so a lane fetches its NC2 columns of one k as
-  // one vector; reloaded into registers at the start of every candidate phase (the gate
-  // accumulators are dead by then), which keeps the kernel at two CTAs per SM
-  __shared__ __align__(16) float w2s[NWARP][KPL][32][NC2];
+  // state_to_state slice: [warp][q][lane][4 k] so a lane fetches four k of its column as one
+  // vector; read in the candidate loop (the gate slice lives in registers for the whole sequence)
+  __shared__ __align__(16) float w2s[NWARP][KQ][32][4];
   __shared__ __align__(8) unsigned long long mbar[2];   // [0]: h arrivals, [1]: h*r arrivals
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kg = lane / CG, cg = lane % CG;
   const int cluster_id = blockIdx.x / CS;
   unsigned rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
@@ -115,28 +133,30 @@ bigru_kernel(BiGruArgs a) {
   const int row0 = (cluster_id >> 1) * RB;    // first batch row of this cluster
   const int ul_warp = warp * NC2;             // first owned unit of this warp, local index
   const int u_warp = rank * UC + ul_warp;     // ... global unit index
+  const int kpeer = (kg * KPG) / UC, koff = (kg * KPG) % UC;   // where this lane's k range sits in hbuf
 
   const float* Wg = dir ? a.Wg_b : a.Wg_f;    // [D, 2D]  cols [update | reset]
   const float* Ws = dir ? a.Ws_b : a.Ws_f;    // [D, D]
   const float* h0 = dir ? a.h0_b : a.h0_f;    // [D]
 
-  // ---- weights -> registers (once) -------------------------------------------------
-  float w1[NC1][KPL];
+  // ---- weights -> registers / shared memory (once) -----------------------------------
+  // gate column cl of the warp (0..NC1): cl < NC2 -> update gate of unit u_warp + cl, else reset gate
+  float w1[CPL1][KPG];
 #pragma unroll
-  for (int kk = 0; kk < KPL; ++kk) {
-    const int k = (kk / 4) * 128 + 4 * lane + (kk % 4);
+  for (int j = 0; j < CPL1; ++j) {
+    const int cl = cg * CPL1 + j;
+    const int col = (cl < NC2) ? (u_warp + cl) : (D + u_warp + (cl - NC2));
 #pragma unroll
-    for (int c = 0; c < NC1; ++c) {
-      const int col = (c < NC2) ? (u_warp + c) : (D + u_warp + (c - NC2));
-      w1[c][kk] = Wg[(long long)k * (2 * D) + col];
-    }
-#pragma unroll
-    for (int c = 0; c < NC2; ++c) w2s[warp][kk][lane][c] = Ws[(long long)k * D + u_warp + c];
+    for (int kk = 0; kk < KPG; ++kk) w1[j][kk] = Wg[(long long)(kg * KPG + kk) * (2 * D) + col];
   }
+#pragma unroll
+  for (int q = 0; q < KQ; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w2s[warp][q][lane][i] = Ws[(long long)(kg * KPG + q * 4 + i) * D + u_warp + cg];
 
   for (int i = tid; i < RB * D; i += NWARP * 32) {
     const int r = i / D, u = i % D;
-    hbuf[u / UC][r][u % UC] = h0[u];
+    hbuf[u / UC][r * UC + u % UC] = h0[u];
   }
   for (int i = tid; i < RB * UC; i += NWARP * 32) stage_h[i / UC][i % UC] = h0[rank * UC + (i % UC)];
 
@@ -147,34 +167,35 @@ bigru_kernel(BiGruArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
 
-  // reduced outputs owned by this lane: phase 1 flattened idx = row*NC1 + c, phase 2 = row*NC2 + c
-  constexpr int O1 = (N1 >= 32) ? N1 / 32 : 1;
-  constexpr int O2 = (N2 >= 32) ? N2 / 32 : 1;
-  constexpr int DUP1 = (N1 >= 32) ? 1 : 32 / N1;   // lanes holding the same value
-  constexpr int DUP2 = (N2 >= 32) ? 1 : 32 / N2;
-  const int base1 = rs_base<N1>(lane), base2 = rs_base<N2>(lane);
-  const bool act1 = (lane % DUP1) == 0, act2 = (lane % DUP2) == 0;
+  // after the reduce-scatter over the kg lanes this lane holds partial-sum index base1 / base2 of
+  // its column group: phase 1 idx = row * CPL1 + j, phase 2 idx = row (duplicated over kg bit 0)
+  const int base1 = rs_base<N1, CG>(lane), base2 = rs_base<N2, CG>(lane);
+  const int row1 = base1 / CPL1, cl1 = cg * CPL1 + base1 % CPL1;      // gate output of this lane
+  const bool is_z = cl1 < NC2;
+  const int ul1 = ul_warp + (is_z ? cl1 : cl1 - NC2);
+  const int row2 = base2, ul2 = ul_warp + cg;                          // candidate output of this lane
+  constexpr int DUP2 = KL / N2;                                        // lanes holding the same candidate sum
+  const bool act2 = DUP2 <= 1 || (kg % DUP2) == 0;
+  static_assert(N1 == KL && N2 <= KL, "one gate sum per lane");
 
   const int T = a.T, B = a.B;
   const long long pre_ld = 6LL * D;                       // [A | Gz | Gr] per direction
   const float* pre_dir = a.pre + (long long)dir * 3 * D;
-
-  float pg[O1], pa[O2], pm[O2];
-  auto prefetch = [&](int t) {
-#pragma unroll
-    for (int j = 0; j < O1; ++j) {
-      const int idx = base1 + j, row = idx / NC1, c = idx % NC1;
-      const int b = row0 + row;
-      const int col = (c < NC2) ? (D + u_warp + c) : (2 * D + u_warp + (c - NC2));
-      pg[j] = (act1 && b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + col) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < O2; ++j) {
-      const int idx = base2 + j, row = idx / NC2, c = idx % NC2;
-      const int b = row0 + row;
-      pa[j] = (act2 && b < B) ? __ldg(pre_dir + ((long long)t * B + b) * pre_ld + u_warp + c) : 0.f;
-      pm[j] = (act2 && b < B && a.mask) ? __ldg(a.mask + (long long)t * a.mask_tstride + b) : 1.f;
-    }
+  const int dt = dir ? -1 : 1;
+  int t = dir ? (T - 1) : 0;
+  // per-lane read pointers into the fork pre-activations, bumped by one time step per iteration
+  const bool ok1 = row0 + row1 < B, ok2 = act2 && (row0 + row2 < B);
+  const float* pg_ptr = pre_dir + ((long long)t * B + row0 + row1) * pre_ld + (is_z ? D : 2 * D) + (ul1 - ul_warp) + u_warp;
+  const float* pa_ptr = pre_dir + ((long long)t * B + row0 + row2) * pre_ld + u_warp + cg;
+  const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + row2 : nullptr;
+  const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
+  float pg = 0.f, pa = 0.f, pm = 1.f;
+  auto prefetch = [&]() {
+    pg = ok1 ? __ldg(pg_ptr) : 0.f;
+    pa = ok2 ? __ldg(pa_ptr) : 0.f;
+    pm = (ok2 && pm_ptr) ? __ldg(pm_ptr) : 1.f;
+    pg_ptr += pre_step; pa_ptr += pre_step;
+    if (pm_ptr) pm_ptr += mask_step;
   };
 
   // every CTA of the cluster must be resident (and its mbarriers initialised) before any
@@ -182,23 +203,17 @@ bigru_kernel(BiGruArgs a) {
   __syncthreads();
   cluster_sync_all();
 
-  const uint32_t hbuf_mine = smem_u32(&hbuf[rank][0][0]);     // same offset in every peer: slot `rank`
-  const uint32_t hrbuf_mine = smem_u32(&hrbuf[rank][0][0]);
+  const uint32_t hbuf_mine = smem_u32(&hbuf[rank][0]);     // same offset in every peer: slot `rank`
+  const uint32_t hrbuf_mine = smem_u32(&hrbuf[rank][0]);
   const uint32_t stage_h_a = smem_u32(&stage_h[0][0]), stage_hr_a = smem_u32(&stage_hr[0][0]);
 
-  int t = dir ? (T - 1) : 0;
-  const int dt = dir ? -1 : 1;
   int sub_phase = dir ? ((T - 1) % a.subsample) : 0;   // t % subsample, maintained incrementally
   int t_out = t / a.subsample;
-  prefetch(t);
+  prefetch();
 
   for (int s = 0; s < T; ++s, t += dt) {
-    float g_cur[O1], a_cur[O2], m_cur[O2];
-#pragma unroll
-    for (int j = 0; j < O1; ++j) g_cur[j] = pg[j];
-#pragma unroll
-    for (int j = 0; j < O2; ++j) { a_cur[j] = pa[j]; m_cur[j] = pm[j]; }
-    if (s + 1 < T) prefetch(t + dt);
+    const float g_cur = pg, a_cur = pa, m_cur = pm;
+    if (s + 1 < T) prefetch();
 
     // h(s-1) from all peers has landed (step 0 uses the locally initialised h0)
     if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
@@ -210,78 +225,60 @@ bigru_kernel(BiGruArgs a) {
     // ---- phase 1: gates of the owned units -----------------------------------------
     float acc1[N1];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float hv[KPL];
+    for (int i = 0; i < N1; ++i) acc1[i] = 0.f;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) {
-        const int k0 = q * 128 + 4 * lane;
-        const float4 v = *reinterpret_cast<const float4*>(&hbuf[k0 / UC][r][k0 % UC]);
-        hv[q * 4 + 0] = v.x; hv[q * 4 + 1] = v.y; hv[q * 4 + 2] = v.z; hv[q * 4 + 3] = v.w;
-      }
+    for (int q = 0; q < KQ; ++q) {
 #pragma unroll
-      for (int c = 0; c < NC1; ++c) {
-        float sacc = 0.f;
+      for (int r = 0; r < RB; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(&hbuf[kpeer][r * UC + koff + q * 4]);
 #pragma unroll
-        for (int kk = 0; kk < KPL; ++kk) sacc = fmaf(hv[kk], w1[c][kk], sacc);
-        acc1[r * NC1 + c] = sacc;
-      }
-    }
-    warp_reduce_scatter<N1>(acc1, lane);
-    if (act1) {
-#pragma unroll
-      for (int j = 0; j < O1; ++j) {
-        const int idx = base1 + j, row = idx / NC1, c = idx % NC1;
-        const float gate = fast_sigmoid(acc1[j] + g_cur[j]);
-        if (c < NC2) {
-          zbuf[row][ul_warp + c] = gate;
-        } else {
-          const int ul = ul_warp + (c - NC2);
-          stage_hr[row][ul] = stage_h[row][ul] * gate;
+        for (int j = 0; j < CPL1; ++j) {
+          float sacc = acc1[r * CPL1 + j];
+          sacc = fmaf(v.x, w1[j][q * 4 + 0], sacc);
+          sacc = fmaf(v.y, w1[j][q * 4 + 1], sacc);
+          sacc = fmaf(v.z, w1[j][q * 4 + 2], sacc);
+          sacc = fmaf(v.w, w1[j][q * 4 + 3], sacc);
+          acc1[r * CPL1 + j] = sacc;
         }
       }
+    }
+    warp_reduce_scatter<N1, CG>(acc1, lane);
+    {
+      const float gate = fast_sigmoid(acc1[0] + g_cur);
+      if (is_z) zbuf[row1][ul1] = gate;
+      else stage_hr[row1][ul1] = stage_h[row1][ul1] * gate;
     }
     fence_async_smem();          // generic-proxy writes of stage_hr -> visible to the bulk-copy engine
     __syncthreads();
     if (warp == 0 && lane < CS) dsmem_bulk_copy(hrbuf_mine, stage_hr_a, SLICE_BYTES, bar_hr, lane);
 
     // ---- phase 2: candidate + blend for the owned units ----------------------------
-    float w2[NC2][KPL];
-#pragma unroll
-    for (int kk = 0; kk < KPL; ++kk)
-#pragma unroll
-      for (int c = 0; c < NC2; ++c) w2[c][kk] = w2s[warp][kk][lane][c];
     mbar_wait(bar_hr, (uint32_t)(s & 1));
     float acc2[N2];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      float hv[KPL];
+    for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
 #pragma unroll
-      for (int q = 0; q < KG; ++q) {
-        const int k0 = q * 128 + 4 * lane;
-        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[k0 / UC][r][k0 % UC]);
-        hv[q * 4 + 0] = v.x; hv[q * 4 + 1] = v.y; hv[q * 4 + 2] = v.z; hv[q * 4 + 3] = v.w;
-      }
+    for (int q = 0; q < KQ; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(&w2s[warp][q][lane][0]);
 #pragma unroll
-      for (int c = 0; c < NC2; ++c) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < KPL; ++kk) sacc = fmaf(hv[kk], w2[c][kk], sacc);
-        acc2[r * NC2 + c] = sacc;
+      for (int r = 0; r < RB; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[kpeer][r * UC + koff + q * 4]);
+        float sacc = acc2[r];
+        sacc = fmaf(v.x, w.x, sacc);
+        sacc = fmaf(v.y, w.y, sacc);
+        sacc = fmaf(v.z, w.z, sacc);
+        sacc = fmaf(v.w, w.w, sacc);
+        acc2[r] = sacc;
       }
     }
-    warp_reduce_scatter<N2>(acc2, lane);
+    warp_reduce_scatter<N2, CG>(acc2, lane);
     if (act2) {
-#pragma unroll
-      for (int j = 0; j < O2; ++j) {
-        const int idx = base2 + j, row = idx / NC2, c = idx % NC2;
-        const int ul = ul_warp + c;
-        const float cand = fast_tanh(acc2[j] + a_cur[j]);
-        const float z = zbuf[row][ul];
-        const float hold = stage_h[row][ul];
-        float hn = cand * z + hold * (1.f - z);
-        hn = m_cur[j] * hn + (1.f - m_cur[j]) * hold;
-        stage_h[row][ul] = hn;
-      }
+      const float cand = fast_tanh(acc2[0] + a_cur);
+      const float z = zbuf[row2][ul2];
+      const float hold = stage_h[row2][ul2];
+      float hn = cand * z + hold * (1.f - z);
+      hn = m_cur * hn + (1.f - m_cur) * hold;
+      stage_h[row2][ul2] = hn;
     }
     fence_async_smem();
     __syncthreads();

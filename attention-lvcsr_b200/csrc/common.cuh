@@ -174,13 +174,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Reduce N per-lane partial sums across the 32 lanes of a warp with a halving
-// exchange: after the call acc[0 .. max(1, N/32)) hold fully reduced values and the
-// returned base says which: acc[j] == sum over lanes of original acc[base + j].
-// When N < 32 the tail stages are plain butterflies, so lane groups hold duplicates.
-template <int NTOT, int n, int o>
+// Reduce N per-lane partial sums across lanes with a halving exchange over the lane-index bits
+// 16, 8, ... down to OMIN (OMIN = 1: all 32 lanes; OMIN = 4: the 8 lanes that differ in bits 2..4,
+// i.e. four independent groups per warp).  After the call acc[0 .. max(1, N / lanes)) hold fully
+// reduced values and the returned base says which: acc[j] == sum over the group of original
+// acc[base + j].  When N < lanes the tail stages are plain butterflies: lane groups hold duplicates.
+template <int NTOT, int n, int o, int OMIN>
 __device__ __forceinline__ void rs_stage(float (&acc)[NTOT], int lane, int& base) {
-  if constexpr (o > 0) {
+  if constexpr (o >= OMIN && o > 0) {
     if constexpr (n > 1) {
       constexpr int h = n / 2;
       const bool up = (lane & o) != 0;
@@ -191,26 +192,26 @@ __device__ __forceinline__ void rs_stage(float (&acc)[NTOT], int lane, int& base
         acc[j] = mine + __shfl_xor_sync(0xffffffffu, theirs, o);
       }
       if (up) base += h;
-      rs_stage<NTOT, h, o / 2>(acc, lane, base);
+      rs_stage<NTOT, h, o / 2, OMIN>(acc, lane, base);
     } else {
       acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
-      rs_stage<NTOT, 1, o / 2>(acc, lane, base);
+      rs_stage<NTOT, 1, o / 2, OMIN>(acc, lane, base);
     }
   }
 }
-template <int N>
+template <int N, int OMIN = 1>
 __device__ __forceinline__ int warp_reduce_scatter(float (&acc)[N], int lane) {
   int base = 0;
-  rs_stage<N, N, 16>(acc, lane, base);
+  rs_stage<N, N, 16, OMIN>(acc, lane, base);
   return base;
 }
 
-// The index base warp_reduce_scatter<N> will return for this lane (pure function of lane).
-template <int N>
+// The index base warp_reduce_scatter<N, OMIN> will return for this lane (pure function of lane).
+template <int N, int OMIN = 1>
 __device__ __forceinline__ int rs_base(int lane) {
   int base = 0, n = N;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 16; o >= OMIN && o > 0; o >>= 1) {
     if (n > 1) {
       n >>= 1;
       if (lane & o) base += n;
