@@ -848,6 +848,10 @@ int lvsr_recognizer_cost_host(lvsr_model* m, const float* x_h, const float* mask
                               const float* lmask_h, int32_t T, int32_t B, int32_t L, float* costs_h, void* stream) {
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(x_h && labels_h && costs_h && T > 0 && B > 0 && L > 0, "recognizer_cost_host: bad arguments");
+  for (long long i = 0; i < (long long)L * B; ++i)       // host memory: the lookup's IndexError, up front
+    LVSR_CHECK(labels_h[i] >= 0 && labels_h[i] < m->cfg.num_phonemes,
+               "recognizer_cost_host: label %lld at [%lld, %lld] outside [0, %d)", (long long)labels_h[i], i / B, i % B,
+               m->cfg.num_phonemes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = 0;
   {

@@ -29,6 +29,14 @@ constexpr int ATT_NW = ATT_NT / 32;
 
 __host__ __device__ inline int att_filter_row(int K) { return K <= 12 ? 12 : 16; }
 
+// sred holds the 8 column groups of the partial context and, earlier in the step, the 16 warps'
+// partial energies.  No shared-memory float atomics: they compile to contended CAS loops AND make
+// the summation order (hence the last bits of every output) vary from run to run.
+__host__ __device__ inline size_t att_red_floats(int E, int tc_cap) {
+  const size_t a = (size_t)8 * E, b = (size_t)ATT_NW * (tc_cap + 16);
+  return a > b ? a : b;
+}
+
 // Shared-memory footprint (floats) of attention_row for a chunk capacity of tc_cap positions.
 __host__ __device__ inline size_t att_smem_floats(int M, int E, int K, int n, int tc_cap, int cs) {
   size_t f = 0;
@@ -41,7 +49,7 @@ __host__ __device__ inline size_t att_smem_floats(int M, int E, int K, int n, in
   f += tc_cap + 16;                               // se
   f += tc_cap + 16;                               // su
   f += 96;                                        // block reduction scratch
-  f += (size_t)8 * E;                             // sred: column groups of partial context
+  f += att_red_floats(E, tc_cap);                 // sred: partial context / per-warp partial energies
   f += (size_t)cs * 4;                            // xs: per-rank scalars (lmax, lsum, anyone, lpos)
   f += (size_t)cs * E;                            // xctx: per-rank partial context (meaningful on rank 0)
   return f + 32;
@@ -98,7 +106,7 @@ __device__ __forceinline__ AttSmem att_carve(float* smem, int M, int E, int K, i
   s.su = p; p += tc_cap + 16;
   s.sblk = p; p += 96;
   p += (4 - ((p - smem) & 3)) & 3;
-  s.sred = p; p += (size_t)8 * E;
+  s.sred = p; p += att_red_floats(E, tc_cap);
   s.xs = p; p += (size_t)cs * 4;
   s.xctx = p; p += (size_t)cs * E;
   return s;
@@ -132,7 +140,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 // NTW: 8-column tiles of the matcher dimension per warp (M = 128 * NTW).
 template <int NTW>
-__device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s, int nt, int t0) {
+__device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s, int nt, int t0, int tc_cap) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
   const int M = a.M;
@@ -154,6 +162,7 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
     vv[j][0] = s.sv[colc]; vv[j][1] = s.sv[colc + 1];
     qq[j][0] = s.sq[colc]; qq[j][1] = s.sq[colc + 1];
   }
+  float* part = s.sred + (size_t)warp * (tc_cap + 16);
   const int ntile = (nt + 15) / 16;
   const float* pbase = a.P + ((long long)(a.b0 + t0) * a.U + a.u) * M + warp * NTW * 8 + 2 * tig;
   const long long prow = (long long)a.U * M;
@@ -192,8 +201,8 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
     ea += __shfl_xor_sync(0xffffffffu, ea, 1); ea += __shfl_xor_sync(0xffffffffu, ea, 2);
     eb += __shfl_xor_sync(0xffffffffu, eb, 1); eb += __shfl_xor_sync(0xffffffffu, eb, 2);
     if (tig == 0) {
-      if (ta < nt) atomicAdd(&s.se[ta], ea);
-      if (tb < nt) atomicAdd(&s.se[tb], eb);
+      part[ta] = ea;       // this warp's private partial sums; rows >= nt land in the 16-row padding
+      part[tb] = eb;
     }
 #pragma unroll
     for (int j = 0; j < NTW; ++j) { pc[j][0] = pn[j][0]; pc[j][1] = pn[j][1]; }
@@ -231,7 +240,6 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       if (prel >= 0 && prel < Tw) val = flow ? ld_flow_f32(a.w_prev + b0 + prel) : a.w_prev[b0 + prel];
       s.salpha[i] = val;
     }
-    for (int i = tid; i < nt + 16; i += NT) s.se[i] = 0.f;
   }
   // attended mask of the owned positions: requested now, consumed after the energies
   float mreg[4];
@@ -307,9 +315,20 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   ATT_STAMP(2);
 
   // ---- energies: e[t] = v . tanh(P[t] + q + F[t] . Wh) on the tensor cores -------------
-  if (M == 512) att_energies<4>(a, s, nt, t0);
-  else if (M == 256) att_energies<2>(a, s, nt, t0);
-  else att_energies<1>(a, s, nt, t0);
+  if (M == 512) att_energies<4>(a, s, nt, t0, tc_cap);
+  else if (M == 256) att_energies<2>(a, s, nt, t0, tc_cap);
+  else att_energies<1>(a, s, nt, t0, tc_cap);
+  __syncthreads();
+  {
+    // e[t] = the 16 warps' partial sums, added in a fixed order
+    const int stride = tc_cap + 16;
+    for (int t = tid; t < nt; t += NT) {
+      float e = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) e += s.sred[(size_t)w * stride + t];
+      s.se[t] = e;
+    }
+  }
   __syncthreads();
   ATT_STAMP(3);
 

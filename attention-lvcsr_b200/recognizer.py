@@ -315,10 +315,19 @@ class SpeechRecognizer(object):
         _lib.check(lib.lvsr_preprocess(h, _ptr(attended), Tp, U, _ptr(out), self._stream()))
         return out
 
+    def _check_labels(self, labels):
+        """Theano's lookup raises IndexError on a symbol outside the table; host arrays are
+        checked here (device tensors are the caller's contract: no hidden synchronisation)."""
+        if isinstance(labels, np.ndarray) and labels.size:
+            lo, hi = int(labels.min()), int(labels.max())
+            if lo < 0 or hi >= self.net["num_phonemes"]:
+                raise ValueError("labels must lie in [0, %d): got %d..%d" % (self.net["num_phonemes"], lo, hi))
+
     def cost_matrix(self, labels, labels_mask, attended, attended_mask, return_all=False):
         """generator.cost_matrix (B/bricks/sequence_generators.py:319-326) on device tensors."""
         torch = self._torch()
         lib, h = _lib.load(), self._require_ready()
+        self._check_labels(labels)
         y = self._dev(labels, torch.int64)
         ym = self._dev(labels_mask, torch.float32)
         att = self._dev(attended, torch.float32)
@@ -352,6 +361,7 @@ class SpeechRecognizer(object):
         x = np.ascontiguousarray(recordings, dtype=np.float32)
         m = None if recordings_mask is None else np.ascontiguousarray(recordings_mask, dtype=np.float32)
         y = np.ascontiguousarray(labels, dtype=np.int64)
+        self._check_labels(y)
         ym = None if labels_mask is None else np.ascontiguousarray(labels_mask, dtype=np.float32)
         T, B, _ = x.shape
         L = y.shape[0]

@@ -95,7 +95,8 @@ int lvsr_preprocess(lvsr_model* m, const float* attended_dev, int32_t Tp, int32_
 
 /* ---- teacher-forced decoder: generator.cost_matrix --------------------------------
  * (libs/blocks/blocks/bricks/sequence_generators.py:254-326).
- * labels int64 [L,B]; labels_mask [L,B] or NULL.  Outputs: costs [L,B]; optional (NULL to
+ * labels int64 [L,B], every entry in [0, num_phonemes) -- device memory, NOT range-checked here
+ * (lvsr_recognizer_cost_host checks its host copy); labels_mask [L,B] or NULL.  Outputs: costs [L,B]; optional (NULL to
  * skip) weights [L,B,T'], energies [L,B,T'], states [L,B,C] (= s_{i-1}),
  * weighted_averages [L,B,E]. */
 int lvsr_cost_matrix(lvsr_model* m, const float* attended_dev, const float* attended_mask_dev,

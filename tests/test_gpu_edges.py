@@ -1,0 +1,136 @@
+"""Edge cases of the hot path on the B200: ragged / degenerate shapes, every readout variant, and
+the error behaviour of the C ABI.  Same bar as test_gpu_parity.py (1e-4 relative against the
+float64 oracle, everything through ctypes -> liblvsr_b200.so)."""
+import numpy as np
+import pytest
+
+from helpers import O, PYRAMID, SMALL, make_recognizer, package, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KEYS = ("costs", "weights", "energies", "states", "weighted_averages")
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _compare_cost(cfg, params, x, m, labels, lm):
+    want = O.recognizer_cost(cfg, params, x, m, labels, lm, return_all=True)
+    rec = make_recognizer(cfg, params)
+    att, attm = rec.encode(x, m)
+    o_att, o_mask = O.encoder(cfg, params, x, m)
+    assert rel_err(att.cpu().numpy(), o_att) < TOL
+    assert np.array_equal(attm.cpu().numpy(), o_mask.astype(np.float32))
+    got = rec.cost_matrix(labels, lm, att, attm, return_all=True)
+    errs = {k: rel_err(got[k].cpu().numpy(), want[k]) for k in KEYS if k in want}
+    for k, e in errs.items():
+        assert e < TOL, (k, e)
+    return errs
+
+
+def test_very_short_utterances_in_a_long_batch():
+    """Lengths 1, 2, 3 and 5 frames next to a full-length utterance: after the 4x pyramid some
+    rows keep a single encoded frame; masked recurrences must carry the state through padding
+    (B/bricks/recurrent.py:224-231 with mask) and the attention must put all weight on it."""
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=13, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=6, T=45, seed=5)
+    lens = [1, 2, 3, 5, 45, 17]
+    for b, n in enumerate(lens):
+        m[:, b] = (np.arange(45) < n)
+    x *= m[:, :, None]
+    errs = _compare_cost(cfg, params, x, m, labels, lm)
+    print("short utterances", errs)
+
+
+@pytest.mark.parametrize("B,T", [(1, 9), (1, 64), (3, 8), (33, 21)])
+def test_odd_batch_and_length_shapes(B, T):
+    """Batches that do not fill a cluster's rows (1, 3), that spill into a second wave of row
+    groups (33) and lengths that are not multiples of the subsampling product."""
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=2, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=B, T=T, seed=B * 100 + T, min_frac=0.3)
+    _compare_cost(cfg, params, x, m, labels, lm)
+
+
+def test_single_decoder_step_and_single_label():
+    _torch()
+    cfg = O.make_config(**SMALL)
+    params = O.init_params(cfg, seed=4, scale=10.0)
+    x, m, _, _ = O.synthetic_batch(cfg, B=4, T=20, seed=8)
+    labels = np.full((1, 4), cfg["eos_label"], dtype=np.int64)
+    lm = np.ones((1, 4))
+    _compare_cost(cfg, params, x, m, labels, lm)
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh", "maxout"])
+@pytest.mark.parametrize("use_states", [True, False])
+def test_readout_variants(activation, use_states):
+    """post_merge activation x use_states_for_readout (lvsr/bricks/recognizer.py:259-279)."""
+    _torch()
+    net = dict(SMALL)
+    net.pop("maxout_pieces")
+    cfg = O.make_config(post_merge_activation=activation, use_states_for_readout=use_states,
+                        maxout_pieces=2 if activation == "maxout" else 1, **net)
+    params = O.init_params(cfg, seed=6, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=5, T=33, seed=9)
+    _compare_cost(cfg, params, x, m, labels, lm)
+
+
+def test_label_mask_freezes_states_after_the_end():
+    """Rows whose labels have ended keep their last state and contribute zero cost
+    (B/bricks/sequence_generators.py:311-319)."""
+    torch = _torch()
+    cfg = O.make_config(**SMALL)
+    params = O.init_params(cfg, seed=7, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=7, T=48, seed=3, min_frac=0.2)
+    rec = make_recognizer(cfg, params)
+    att, attm = rec.encode(x, m)
+    got = rec.cost_matrix(labels, lm, att, attm, return_all=True)
+    states = got["states"].cpu().numpy()          # [L, B, C]
+    costs = got["costs"].cpu().numpy()
+    L = labels.shape[0]
+    for b in range(labels.shape[1]):
+        n = int(lm[:, b].sum())
+        if n < L:
+            assert np.all(costs[n:, b] == 0.0)
+            assert np.array_equal(states[n:, b], np.broadcast_to(states[n, b], states[n:, b].shape))
+
+
+def test_repeated_calls_are_bit_identical():
+    """No atomics with run-dependent order anywhere on the path: two calls give the same bits."""
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=9, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=10, T=70, seed=12)
+    rec = make_recognizer(cfg, params)
+    a1, am = rec.encode(x, m)
+    a2, _ = rec.encode(x, m)
+    assert bool((a1 == a2).all())
+    r1 = rec.cost_matrix(labels, lm, a1, am, return_all=True)
+    r2 = rec.cost_matrix(labels, lm, a1, am, return_all=True)
+    for k in KEYS:
+        assert bool((r1[k] == r2[k]).all()), k
+
+
+def test_shape_errors_are_reported_not_crashed():
+    _torch()
+    pkg = package()
+    cfg = O.make_config(**SMALL)
+    params = O.init_params(cfg, seed=1, scale=10.0)
+    rec = make_recognizer(cfg, params)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=3, T=16, seed=1)
+    with pytest.raises((RuntimeError, ValueError)):
+        rec.encode(x[:, :, :-1], m)                     # wrong feature width
+    att, attm = rec.encode(x, m)
+    bad = labels.copy()
+    bad[0, 0] = cfg["num_phonemes"] + 5                   # label outside the vocabulary
+    with pytest.raises((RuntimeError, ValueError)):
+        rec.cost_matrix(bad, lm, att, attm)
+    assert pkg is not None
