@@ -5,33 +5,30 @@
 // child of Bidirectional (B/bricks/recurrent.py:224-231, 608-620, 655-663) plus the
 // x[::k] subsampling of Encoder.apply (lvsr/bricks/__init__.py:75-77).
 //
-// B200 mapping (the recurrence is latency-bound: two DEPENDENT [rows,D]x[D,*]
-// products per step, T sequential steps):
-//   * batch rows are independent -> a thread-block CLUSTER of CS CTAs owns RB rows of
-//     one direction; clusters never talk to each other (no grid-wide barrier).
-//   * inside a cluster the hidden units are split: CTA `rank` owns UC = D/CS units and
-//     keeps its slice of state_to_gates / state_to_state IN REGISTERS for the whole
-//     sequence -- weights are read from HBM once per layer.
-//   * per step: gates for the owned units (needs all of h), all-gather of h*r, candidate
-//     for the owned units, all-gather of h'.  Each all-gather is CS bulk DSMEM copies
-//     (cp.async.bulk shared::cta -> shared::cluster, 1 KB each) that complete on the
-//     RECEIVER's mbarrier (complete_tx): no fence, no cluster barrier in the loop; the
-//     consumer simply waits for RB*D*4 bytes to land.  h never leaves the chip.
-//   * each warp splits K over its 32 lanes and finishes with a halving reduce-scatter.
+// B200 mapping (two DEPENDENT [rows,D]x[D,*] products per step, T sequential steps):
+//   * batch rows are independent -> a thread-block CLUSTER of CS CTAs owns RB = 4 rows of one
+//     direction; clusters never talk to each other (no grid-wide barrier).
+//   * inside a cluster the hidden units are split: CTA `rank` owns UC = D/CS units, each of its
+//     warps 4 of them; the state_to_gates slice stays IN REGISTERS for the whole sequence, the
+//     state_to_state slice in shared memory -- weights are read from HBM once per layer.
+//   * per step: gates for the owned units (needs all of h), all-gather of h*r, candidate for the
+//     owned units, all-gather of h'.  An all-gather is one `st.async` per lane: 16 bytes go from
+//     registers straight into the receiver's shared memory and credit the RECEIVER's mbarrier
+//     (complete_tx); no staging buffer, no proxy fence, no CTA or cluster barrier in the loop --
+//     a warp only ever waits for "all RB*D*4 bytes of h (or h*r) have landed".  h never leaves the chip.
+//   * inside a warp k is split over 8 lanes and the columns over the other 4 (see the kernel);
+//     everything the epilogues need from other lanes travels by shuffle.
 //   * the fork pre-activations of step t+1 are prefetched into registers during step t.
-// r1a -> r1b: 4-byte remote stores + barrier.cluster.arrive.release cost 30 % of the
-// kernel in the fence (profiles/r1a_summary.md); replaced by the scheme above.
+// History (profiles/): r1a 4-byte remote stores + barrier.cluster (30 % of the kernel in the fence,
+// 8.6 us/step) -> bulk DSMEM copies + mbarrier (3.07 us) -> this layout (2.76 us; the kernel is bound
+// by the SM's issue slots at ~50 % utilisation: 714 instructions per warp and step, 386 of them FFMA).
 #include "kernels.h"
 
 namespace lvsr {
 
 namespace {
 
-// Two CTAs are co-resident per SM (256 threads, <=128 registers each): they belong to
-// different clusters, i.e. independent recurrences, so one chain's exchange latency is
-// covered by the other chain's arithmetic.
 constexpr int RB = 4;        // batch rows per cluster
-constexpr int NWARP = 8;     // warps per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -66,18 +63,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1ull << 24)) __trap();   // a lost transfer must fail the launch, not hang the GPU
   }
 }
-// local shared memory -> shared memory of CTA `rank`, completes on that CTA's mbarrier
-__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_local, uint32_t src_local, uint32_t bytes,
-                                                uint32_t bar_local, int rank) {
-  const uint32_t dst = map_to_rank(dst_local, rank);
-  const uint32_t bar = map_to_rank(bar_local, rank);
-  asm volatile(
-      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
-      "r"(src_local), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+// 16 bytes straight from registers into the shared memory of another CTA of the cluster; the
+// RECEIVER's mbarrier is credited with the bytes when they land (no staging buffer, no proxy
+// fence, no CTA barrier on the sender).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float y, float z, float w,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(
+                   remote_addr),
+               "f"(x), "f"(y), "f"(z), "f"(w), "r"(remote_bar)
+               : "memory");
 }
 
 // D: hidden units per direction; CS: CTAs per cluster.
@@ -90,8 +84,13 @@ __device__ __forceinline__ void fence_async_smem() {
 // A lane therefore accumulates RB x 2 gate sums and RB x 1 candidate sums over its D/8 k values and
 // the cross-lane reduction runs over the 8 kg-lanes only: 7 + 4 exchanges per step instead of
 // 31 + 15 over all 32 lanes.
-template <int D, int CS>
-__global__ void __launch_bounds__(NWARP * 32, 2)
+//
+// Two shapes: <D, 8 or 4 CTAs, 8 warps> = 256 threads, two CTAs (two different clusters) per SM,
+// and <256, 4 CTAs, 16 warps> = 512 threads, one CTA per SM.  At the metric batch the second wins:
+// with two clusters sharing every SM any stall of one CTA delays its whole 8-CTA cluster twice per
+// step (1.73 us per step when a narrow CTA owns its SM vs 3.07 us when two share one).
+template <int D, int CS, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, NWARP == 8 ? 2 : 1)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
   constexpr int KL = 8;               // lanes that split k
@@ -104,24 +103,20 @@ bigru_kernel(BiGruArgs a) {
   constexpr int CPL2 = NC2 / CG;      // candidate columns per lane
   static_assert(D % (CS * NWARP) == 0 && D % (4 * KL) == 0, "unsupported D / cluster size");
   static_assert(NC2 % CG == 0 && CPL2 == 1, "one candidate column per lane");
-  static_assert(UC % KPG == 0 || KPG % UC == 0, "a lane's k range must not straddle peer slices unevenly");
-  static_assert(KPG <= UC, "a lane's k range sits inside one peer slice");
+  static_assert(KPG <= 32 && 32 % KPG == 0, "a lane's k range sits inside one 32-unit chunk");
   constexpr int N1 = RB * CPL1, N2 = RB * CPL2;        // per-lane partial sums of the two phases
-  constexpr uint32_t SLICE_BYTES = RB * UC * sizeof(float);
   constexpr uint32_t FULL_BYTES = RB * D * sizeof(float);
 
-  // peer-major: slot p holds the [RB][UC] slice owned by CTA p -> one bulk copy per peer.  Slots
-  // are padded by 16 bytes: the 8 kg lanes of a warp read 8 different slots at the same offset,
-  // which without the pad is an 8-way bank conflict on every load (measured: 2x the step time).
-  constexpr int SLOT = RB * UC + 4;
-  __shared__ __align__(128) float hbuf[CS][SLOT];       // h, all units
-  __shared__ __align__(128) float hrbuf[CS][SLOT];      // h * reset, all units
-  __shared__ __align__(128) float stage_h[RB][UC];      // own slice of h (source of the copies)
-  __shared__ __align__(128) float stage_hr[RB][UC];     // own slice of h * reset
-  __shared__ float zbuf[RB][UC];                        // update gates of the owned units
+  // h and h*r of all units, in chunks of 32 units: chunk c holds [RB][32] floats + 16 bytes of pad.
+  // The 8 kg lanes of a warp read 8 different chunks (or half chunks) at the same offset; without
+  // the pad that is an 8-way bank conflict on every load (measured: 2x the step time).
+  constexpr int CH = 32, NCH = D / CH, SLOT = RB * CH + 4;
+  __shared__ __align__(128) float hbuf[NCH][SLOT];
+  __shared__ __align__(128) float hrbuf[NCH][SLOT];
   // state_to_state slice: [warp][q][lane][4 k] so a lane fetches four k of its column as one
   // vector; read in the candidate loop (the gate slice lives in registers for the whole sequence)
-  __shared__ __align__(16) float w2s[NWARP][KQ][32][4];
+  extern __shared__ __align__(16) float w2s_dyn[];
+  float (*w2s)[KQ][32][4] = reinterpret_cast<float (*)[KQ][32][4]>(w2s_dyn);
   __shared__ __align__(8) unsigned long long mbar[2];   // [0]: h arrivals, [1]: h*r arrivals
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -133,7 +128,7 @@ bigru_kernel(BiGruArgs a) {
   const int row0 = (cluster_id >> 1) * RB;    // first batch row of this cluster
   const int ul_warp = warp * NC2;             // first owned unit of this warp, local index
   const int u_warp = rank * UC + ul_warp;     // ... global unit index
-  const int kpeer = (kg * KPG) / UC, koff = (kg * KPG) % UC;   // where this lane's k range sits in hbuf
+  const int kpeer = (kg * KPG) / 32, koff = (kg * KPG) % 32;   // chunk and offset of this lane's k range
 
   const float* Wg = dir ? a.Wg_b : a.Wg_f;    // [D, 2D]  cols [update | reset]
   const float* Ws = dir ? a.Ws_b : a.Ws_f;    // [D, D]
@@ -156,27 +151,42 @@ bigru_kernel(BiGruArgs a) {
 
   for (int i = tid; i < RB * D; i += NWARP * 32) {
     const int r = i / D, u = i % D;
-    hbuf[u / UC][r * UC + u % UC] = h0[u];
+    hbuf[u / CH][r * CH + u % CH] = h0[u];
   }
-  for (int i = tid; i < RB * UC; i += NWARP * 32) stage_h[i / UC][i % UC] = h0[rank * UC + (i % UC)];
 
+  // Lane roles after the reduce-scatters over the kg lanes (kg = lane >> 2, cg = lane & 3):
+  //   gate sum      (row1 = kg >> 1, column cl1 = cg * 2 + (kg & 1)): cl1 < NC2 update gate of unit cl1,
+  //                                                                  else reset gate of unit cl1 - NC2
+  //   candidate sum (row2 = kg >> 1, unit cg), duplicated in the lane pair kg, kg ^ 1
+  // h of (row, unit) lives in a register of lane 8 * row + unit (and its duplicate); everything
+  // the epilogues need from other lanes comes by shuffle, nothing goes through shared memory.
+  static_assert(RB == 4 && NC2 == 4 && CPL1 == 2, "lane roles below assume 4 rows x 4 units per warp");
+  const int row1 = kg >> 1, cl1 = cg * CPL1 + (kg & 1);
+  const bool is_z = cl1 < NC2;
+  const int unit1 = is_z ? cl1 : cl1 - NC2;
+  const int row2 = kg >> 1, unit2 = cg;
+  const int src_hold = 8 * row1 + unit1;                                  // h of my reset gate's unit
+  const int src_z = (2 * row2 + (unit2 & 1)) * 4 + (unit2 >> 1);           // update gate of my candidate's unit
+  // sender role: lane = rowg * 8 + peer ships row rowg of this warp's 4 units to CTA `peer`
+  const int rowg = lane >> 3, peer = lane & 7;
+  const bool sender = peer < CS;
+  int src_hr[4], src_h[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    src_hr[u] = (2 * rowg + (u & 1)) * 4 + 2 + (u >> 1);
+    src_h[u] = 8 * rowg + u;
+  }
   const uint32_t bar_h = smem_u32(&mbar[0]), bar_hr = smem_u32(&mbar[1]);
+  // where this warp's 4 units of row rowg land in the receiver
+  const uint32_t dst_h = map_to_rank(smem_u32(&hbuf[u_warp / CH][rowg * CH + u_warp % CH]), sender ? peer : 0);
+  const uint32_t dst_hr = map_to_rank(smem_u32(&hrbuf[u_warp / CH][rowg * CH + u_warp % CH]), sender ? peer : 0);
+  const uint32_t rbar_h = map_to_rank(bar_h, sender ? peer : 0), rbar_hr = map_to_rank(bar_hr, sender ? peer : 0);
   if (tid == 0) {
     mbar_init(bar_h, 1);
     mbar_init(bar_hr, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-
-  // after the reduce-scatter over the kg lanes this lane holds partial-sum index base1 / base2 of
-  // its column group: phase 1 idx = row * CPL1 + j, phase 2 idx = row (duplicated over kg bit 0)
-  const int base1 = rs_base<N1, CG>(lane), base2 = rs_base<N2, CG>(lane);
-  const int row1 = base1 / CPL1, cl1 = cg * CPL1 + base1 % CPL1;      // gate output of this lane
-  const bool is_z = cl1 < NC2;
-  const int ul1 = ul_warp + (is_z ? cl1 : cl1 - NC2);
-  const int row2 = base2, ul2 = ul_warp + cg;                          // candidate output of this lane
-  constexpr int DUP2 = KL / N2;                                        // lanes holding the same candidate sum
-  const bool act2 = DUP2 <= 1 || (kg % DUP2) == 0;
-  static_assert(N1 == KL && N2 <= KL, "one gate sum per lane");
+  float h_own = h0[u_warp + unit2];                                        // h(row2, unit2), same for every row at t = -1
 
   const int T = a.T, B = a.B;
   const long long pre_ld = 6LL * D;                       // [A | Gz | Gr] per direction
@@ -184,9 +194,9 @@ bigru_kernel(BiGruArgs a) {
   const int dt = dir ? -1 : 1;
   int t = dir ? (T - 1) : 0;
   // per-lane read pointers into the fork pre-activations, bumped by one time step per iteration
-  const bool ok1 = row0 + row1 < B, ok2 = act2 && (row0 + row2 < B);
-  const float* pg_ptr = pre_dir + ((long long)t * B + row0 + row1) * pre_ld + (is_z ? D : 2 * D) + (ul1 - ul_warp) + u_warp;
-  const float* pa_ptr = pre_dir + ((long long)t * B + row0 + row2) * pre_ld + u_warp + cg;
+  const bool ok1 = row0 + row1 < B, ok2 = row0 + row2 < B;
+  const float* pg_ptr = pre_dir + ((long long)t * B + row0 + row1) * pre_ld + (is_z ? D : 2 * D) + u_warp + unit1;
+  const float* pa_ptr = pre_dir + ((long long)t * B + row0 + row2) * pre_ld + u_warp + unit2;
   const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + row2 : nullptr;
   const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
   float pg = 0.f, pa = 0.f, pm = 1.f;
@@ -203,9 +213,6 @@ bigru_kernel(BiGruArgs a) {
   __syncthreads();
   cluster_sync_all();
 
-  const uint32_t hbuf_mine = smem_u32(&hbuf[rank][0]);     // same offset in every peer: slot `rank`
-  const uint32_t hrbuf_mine = smem_u32(&hrbuf[rank][0]);
-  const uint32_t stage_h_a = smem_u32(&stage_h[0][0]), stage_hr_a = smem_u32(&stage_hr[0][0]);
 
   int sub_phase = dir ? ((T - 1) % a.subsample) : 0;   // t % subsample, maintained incrementally
   int t_out = t / a.subsample;
@@ -230,7 +237,7 @@ bigru_kernel(BiGruArgs a) {
     for (int q = 0; q < KQ; ++q) {
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&hbuf[kpeer][r * UC + koff + q * 4]);
+        const float4 v = *reinterpret_cast<const float4*>(&hbuf[kpeer][r * CH + koff + q * 4]);
 #pragma unroll
         for (int j = 0; j < CPL1; ++j) {
           float sacc = acc1[r * CPL1 + j];
@@ -243,14 +250,13 @@ bigru_kernel(BiGruArgs a) {
       }
     }
     warp_reduce_scatter<N1, CG>(acc1, lane);
+    const float gate = fast_sigmoid(acc1[0] + g_cur);                    // z or r of (row1, unit1)
+    const float hr_mine = __shfl_sync(0xffffffffu, h_own, src_hold) * gate;   // meaningful on reset-gate lanes
     {
-      const float gate = fast_sigmoid(acc1[0] + g_cur);
-      if (is_z) zbuf[row1][ul1] = gate;
-      else stage_hr[row1][ul1] = stage_h[row1][ul1] * gate;
+      const float x = __shfl_sync(0xffffffffu, hr_mine, src_hr[0]), y = __shfl_sync(0xffffffffu, hr_mine, src_hr[1]);
+      const float z = __shfl_sync(0xffffffffu, hr_mine, src_hr[2]), w = __shfl_sync(0xffffffffu, hr_mine, src_hr[3]);
+      if (sender) st_async_v4(dst_hr, x, y, z, w, rbar_hr);
     }
-    fence_async_smem();          // generic-proxy writes of stage_hr -> visible to the bulk-copy engine
-    __syncthreads();
-    if (warp == 0 && lane < CS) dsmem_bulk_copy(hrbuf_mine, stage_hr_a, SLICE_BYTES, bar_hr, lane);
 
     // ---- phase 2: candidate + blend for the owned units ----------------------------
     mbar_wait(bar_hr, (uint32_t)(s & 1));
@@ -262,7 +268,7 @@ bigru_kernel(BiGruArgs a) {
       const float4 w = *reinterpret_cast<const float4*>(&w2s[warp][q][lane][0]);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[kpeer][r * UC + koff + q * 4]);
+        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[kpeer][r * CH + koff + q * 4]);
         float sacc = acc2[r];
         sacc = fmaf(v.x, w.x, sacc);
         sacc = fmaf(v.y, w.y, sacc);
@@ -272,28 +278,18 @@ bigru_kernel(BiGruArgs a) {
       }
     }
     warp_reduce_scatter<N2, CG>(acc2, lane);
-    if (act2) {
+    {
+      const float zg = __shfl_sync(0xffffffffu, gate, src_z);            // update gate of (row2, unit2)
       const float cand = fast_tanh(acc2[0] + a_cur);
-      const float z = zbuf[row2][ul2];
-      const float hold = stage_h[row2][ul2];
-      float hn = cand * z + hold * (1.f - z);
-      hn = m_cur * hn + (1.f - m_cur) * hold;
-      stage_h[row2][ul2] = hn;
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (warp == 0 && lane < CS) dsmem_bulk_copy(hbuf_mine, stage_h_a, SLICE_BYTES, bar_h, lane);
-    if (sub_phase == 0 && warp == 1) {
-      // coalesced store of the owned slice: RB rows x UC floats (128 B per row)
-      constexpr int F4 = RB * UC / 4;
-      for (int i = lane; i < F4; i += 32) {
-        const int row = i / (UC / 4), c4 = i % (UC / 4);
-        const int b = row0 + row;
-        if (b < B) {
-          const float4 v = *reinterpret_cast<const float4*>(&stage_h[row][c4 * 4]);
-          *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + b) * (2 * D) + dir * D + rank * UC + c4 * 4) = v;
-        }
-      }
+      float hn = cand * zg + h_own * (1.f - zg);
+      hn = m_cur * hn + (1.f - m_cur) * h_own;
+      h_own = hn;
+      const float x = __shfl_sync(0xffffffffu, hn, src_h[0]), y = __shfl_sync(0xffffffffu, hn, src_h[1]);
+      const float z = __shfl_sync(0xffffffffu, hn, src_h[2]), w = __shfl_sync(0xffffffffu, hn, src_h[3]);
+      if (sender) st_async_v4(dst_h, x, y, z, w, rbar_h);
+      if (sub_phase == 0 && peer == 0 && row0 + rowg < B)
+        *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
+            make_float4(x, y, z, w);
     }
     // advance t % subsample and t / subsample without dividing
     if (dir == 0) {
@@ -307,13 +303,20 @@ bigru_kernel(BiGruArgs a) {
   cluster_sync_all();
 }
 
-template <int D, int CS>
+template <int D, int CS, int NWARP>
 int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
+  constexpr size_t W2S_BYTES = (size_t)NWARP * (D / 8 / 4) * 32 * 4 * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_kernel<D, CS, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)W2S_BYTES));
+    configured = true;
+  }
   const int groups = ceil_div(a.B, RB);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS * groups * 2);
   cfg.blockDim = dim3(NWARP * 32);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = W2S_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -322,21 +325,67 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_kernel<D, CS>, a));
+  LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_kernel<D, CS, NWARP>, a));
   g_launch_count++;
   return 0;
+}
+
+int bigru_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// how many <256, 4, 16> clusters the device holds at once (a GPC takes floor(SMs / 4) of them; the
+// count differs between parts with different floor-sweeping, so ask the driver)
+int wide_clusters_resident() {
+  static int n = -1;
+  if (n < 0) {
+    constexpr size_t W2S_BYTES = (size_t)16 * (256 / 8 / 4) * 32 * 4 * sizeof(float);
+    cudaFuncSetAttribute(bigru_kernel<256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2S_BYTES);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(16 * 32);
+    cfg.dynamicSmemBytes = W2S_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int k = 0;
+    if (cudaOccupancyMaxActiveClusters(&k, bigru_kernel<256, 4, 16>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      k = 0;
+    }
+    n = k;
+  }
+  return n;
 }
 
 }  // namespace
 
 bool bigru_supported(int D) { return D == 128 || D == 256; }
 
+
+
 int bigru_layer(const BiGruArgs& a, cudaStream_t stream) {
   ProfScope prof("bigru", stream);
   if (a.T <= 0 || a.B <= 0) return 0;
+  // D = 256: 4 CTAs x 16 warps (one CTA per SM) as soon as the 8 x 8 shape would have to put two
+  // CTAs on an SM, as long as every such cluster still gets SMs of its own
+  const int groups = ceil_div(a.B, RB);
+  bool wide = a.D == 256 && 8 * groups * 2 > bigru_sm_count() && groups * 2 <= wide_clusters_resident();
+  if (const char* e = getenv("LVSR_BIGRU_WIDE")) wide = a.D == 256 && atoi(e) != 0;
   switch (a.D) {
-    case 128: return launch_bigru<128, 4>(a, stream);
-    case 256: return launch_bigru<256, 8>(a, stream);
+    case 128: return launch_bigru<128, 4, 8>(a, stream);
+    case 256: return wide ? launch_bigru<256, 4, 16>(a, stream) : launch_bigru<256, 8, 8>(a, stream);
     default:
       return set_error("bigru: unsupported hidden size %d (supported: 128, 256)", a.D);
   }
