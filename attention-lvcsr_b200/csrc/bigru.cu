@@ -30,6 +30,11 @@ namespace {
 
 constexpr int RB = 4;        // batch rows per cluster
 
+// LVSR_BIGRU_TRACE=1: thread 0 of CTA 0 accumulates the SM clock spent in each section of a step
+// (wait h, gate product, gate epilogue + send, wait h*r, candidate product, epilogue + send).
+__device__ unsigned long long g_bigru_trace[8];
+__device__ int g_bigru_trace_on = 0;
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -136,13 +141,17 @@ bigru_kernel(BiGruArgs a) {
 
   // ---- weights -> registers / shared memory (once) -----------------------------------
   // gate column cl of the warp (0..NC1): cl < NC2 -> update gate of unit u_warp + cl, else reset gate
-  float w1[CPL1][KPG];
+  // packed pairs (k, k+1): one FFMA2 (fma.rn.f32x2) advances the even-k and the odd-k partial sum
+  // of a column at once -- h arrives as (k, k+1) register pairs from the 16-byte loads anyway
+  unsigned long long w1[CPL1][KPG / 2];
 #pragma unroll
   for (int j = 0; j < CPL1; ++j) {
     const int cl = cg * CPL1 + j;
     const int col = (cl < NC2) ? (u_warp + cl) : (D + u_warp + (cl - NC2));
 #pragma unroll
-    for (int kk = 0; kk < KPG; ++kk) w1[j][kk] = Wg[(long long)(kg * KPG + kk) * (2 * D) + col];
+    for (int kk = 0; kk < KPG / 2; ++kk)
+      w1[j][kk] = pack_f32x2(Wg[(long long)(kg * KPG + 2 * kk) * (2 * D) + col],
+                             Wg[(long long)(kg * KPG + 2 * kk + 1) * (2 * D) + col]);
   }
 #pragma unroll
   for (int q = 0; q < KQ; ++q)
@@ -218,9 +227,21 @@ bigru_kernel(BiGruArgs a) {
   int t_out = t / a.subsample;
   prefetch();
 
+  const bool tracer = g_bigru_trace_on && blockIdx.x == 0 && tid == 0;
+  unsigned long long tr[6] = {0, 0, 0, 0, 0, 0};
+  long long tc = 0;
+#define BG_STAMP(j)                          \
+  do {                                       \
+    if (tracer) {                            \
+      const long long now = clock64();       \
+      tr[j] += (unsigned long long)(now - tc); \
+      tc = now;                              \
+    }                                        \
+  } while (0)
   for (int s = 0; s < T; ++s, t += dt) {
     const float g_cur = pg, a_cur = pa, m_cur = pm;
     if (s + 1 < T) prefetch();
+    if (tracer) tc = clock64();
 
     // h(s-1) from all peers has landed (step 0 uses the locally initialised h0)
     if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
@@ -228,27 +249,32 @@ bigru_kernel(BiGruArgs a) {
       mbar_arm(bar_h, FULL_BYTES);    // arrivals of h'(s)
       mbar_arm(bar_hr, FULL_BYTES);   // arrivals of (h*r)(s)
     }
+    BG_STAMP(0);
 
     // ---- phase 1: gates of the owned units -----------------------------------------
     float acc1[N1];
+    {
+      unsigned long long ap[N1];
 #pragma unroll
-    for (int i = 0; i < N1; ++i) acc1[i] = 0.f;
+      for (int i = 0; i < N1; ++i) ap[i] = 0ull;
 #pragma unroll
-    for (int q = 0; q < KQ; ++q) {
+      for (int q = 0; q < KQ; ++q) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&hbuf[kpeer][r * CH + koff + q * 4]);
+        for (int r = 0; r < RB; ++r) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&hbuf[kpeer][r * CH + koff + q * 4]);
 #pragma unroll
-        for (int j = 0; j < CPL1; ++j) {
-          float sacc = acc1[r * CPL1 + j];
-          sacc = fmaf(v.x, w1[j][q * 4 + 0], sacc);
-          sacc = fmaf(v.y, w1[j][q * 4 + 1], sacc);
-          sacc = fmaf(v.z, w1[j][q * 4 + 2], sacc);
-          sacc = fmaf(v.w, w1[j][q * 4 + 3], sacc);
-          acc1[r * CPL1 + j] = sacc;
+          for (int j = 0; j < CPL1; ++j) {
+            unsigned long long sacc = ap[r * CPL1 + j];
+            sacc = ffma2(v.x, w1[j][q * 2 + 0], sacc);
+            sacc = ffma2(v.y, w1[j][q * 2 + 1], sacc);
+            ap[r * CPL1 + j] = sacc;
+          }
         }
       }
+#pragma unroll
+      for (int i = 0; i < N1; ++i) acc1[i] = sum_f32x2(ap[i]);
     }
+    BG_STAMP(1);
     warp_reduce_scatter<N1, CG>(acc1, lane);
     const float gate = fast_sigmoid(acc1[0] + g_cur);                    // z or r of (row1, unit1)
     const float hr_mine = __shfl_sync(0xffffffffu, h_own, src_hold) * gate;   // meaningful on reset-gate lanes
@@ -258,25 +284,31 @@ bigru_kernel(BiGruArgs a) {
       if (sender) st_async_v4(dst_hr, x, y, z, w, rbar_hr);
     }
 
+    BG_STAMP(2);
     // ---- phase 2: candidate + blend for the owned units ----------------------------
     mbar_wait(bar_hr, (uint32_t)(s & 1));
+    BG_STAMP(3);
     float acc2[N2];
+    {
+      unsigned long long ap[N2];
 #pragma unroll
-    for (int i = 0; i < N2; ++i) acc2[i] = 0.f;
+      for (int i = 0; i < N2; ++i) ap[i] = 0ull;
 #pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      const float4 w = *reinterpret_cast<const float4*>(&w2s[warp][q][lane][0]);
+      for (int q = 0; q < KQ; ++q) {
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(&w2s[warp][q][lane][0]);
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&hrbuf[kpeer][r * CH + koff + q * 4]);
-        float sacc = acc2[r];
-        sacc = fmaf(v.x, w.x, sacc);
-        sacc = fmaf(v.y, w.y, sacc);
-        sacc = fmaf(v.z, w.z, sacc);
-        sacc = fmaf(v.w, w.w, sacc);
-        acc2[r] = sacc;
+        for (int r = 0; r < RB; ++r) {
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&hrbuf[kpeer][r * CH + koff + q * 4]);
+          unsigned long long sacc = ap[r];
+          sacc = ffma2(v.x, w.x, sacc);
+          sacc = ffma2(v.y, w.y, sacc);
+          ap[r] = sacc;
+        }
       }
+#pragma unroll
+      for (int i = 0; i < N2; ++i) acc2[i] = sum_f32x2(ap[i]);
     }
+    BG_STAMP(4);
     warp_reduce_scatter<N2, CG>(acc2, lane);
     {
       const float zg = __shfl_sync(0xffffffffu, gate, src_z);            // update gate of (row2, unit2)
@@ -291,12 +323,19 @@ bigru_kernel(BiGruArgs a) {
         *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
             make_float4(x, y, z, w);
     }
+    BG_STAMP(5);
     // advance t % subsample and t / subsample without dividing
     if (dir == 0) {
       if (++sub_phase == a.subsample) { sub_phase = 0; ++t_out; }
     } else {
       if (sub_phase == 0) { sub_phase = a.subsample - 1; --t_out; } else { --sub_phase; }
     }
+  }
+#undef BG_STAMP
+  if (tracer) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) g_bigru_trace[j] = tr[j];
+    g_bigru_trace[6] = (unsigned long long)T;
   }
   // drain: the last h' copies must have landed everywhere before any CTA may exit
   mbar_wait(bar_h, (uint32_t)((T - 1) & 1));
@@ -325,8 +364,23 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const bool trace = getenv("LVSR_BIGRU_TRACE") != nullptr;
+  if (trace) {
+    const int on = 1;
+    LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_bigru_trace_on, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream));
+  }
   LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_kernel<D, CS, NWARP>, a));
   g_launch_count++;
+  if (trace) {
+    unsigned long long h[8] = {0};
+    LVSR_CUDA_OK(cudaMemcpyFromSymbolAsync(h, g_bigru_trace, sizeof(h), 0, cudaMemcpyDeviceToHost, stream));
+    LVSR_CUDA_OK(cudaStreamSynchronize(stream));
+    const double n = h[6] ? (double)h[6] : 1.0;
+    fprintf(stderr,
+            "[bigru trace] <%d,%d,%d> T=%llu cycles/step: wait_h=%.0f gates=%.0f gate_epi+send=%.0f wait_hr=%.0f "
+            "cand=%.0f cand_epi+send=%.0f\n",
+            D, CS, NWARP, h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
+  }
   return 0;
 }
 
