@@ -81,14 +81,16 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float
 
 // D: hidden units per direction; CS: CTAs per cluster.
 //
-// Work split inside a warp (the kernel is bound by instruction issue, see profiles/r1f_summary.md,
-// so the layout minimises instructions that are not FFMAs): lane = kg * CG + cg.
-//   kg (KL = 8 groups)  owns the k range [kg * D/8, +D/8) of both products -- exactly the slice of
-//                       h that one or half a peer CTA delivers, 128 contiguous bytes per row;
-//   cg (CG = 4 groups)  owns NC1/4 of the warp's gate columns and NC2/4 of its candidate columns.
-// A lane therefore accumulates RB x 2 gate sums and RB x 1 candidate sums over its D/8 k values and
-// the cross-lane reduction runs over the 8 kg-lanes only: 7 + 4 exchanges per step instead of
-// 31 + 15 over all 32 lanes.
+// Work split inside a warp: lane = kg * CG + cg.
+//   kg (KL = 16 groups) owns the k range [kg * D/16, +D/16) of both products;
+//   cg (CG = 2 groups)  owns half of the warp's gate columns (cg 0: the 4 update gates, cg 1: the 4
+//                       reset gates) and half of its candidate columns.
+// A lane accumulates RB x 4 gate sums and RB x 2 candidate sums over its D/16 k values; the
+// cross-lane reduction runs over the 16 kg-lanes: 15 + 8 exchanges per step.  The split is a
+// measured trade (LVSR_BIGRU_TRACE): every lane must read its k range of h for all rows, and the
+// shared-memory RETURN path (128 B/clk/SM, 4 cycles per warp-wide 16-byte load) is what bounds a
+// phase -- k over 8 lanes: 72 loads per warp and step, 4.6 k cycles; k over 32 lanes: 24 loads but
+// 46 exchanges and ~1000 instructions per warp and step (issue-bound); 16 lanes sits between.
 //
 // Two shapes: <D, 8 or 4 CTAs, 8 warps> = 256 threads, two CTAs (two different clusters) per SM,
 // and <256, 4 CTAs, 16 warps> = 512 threads, one CTA per SM.  At the metric batch the second wins:
@@ -98,7 +100,7 @@ template <int D, int CS, int NWARP>
 __global__ void __launch_bounds__(NWARP * 32, NWARP == 8 ? 2 : 1)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
-  constexpr int KL = 8;               // lanes that split k
+  constexpr int KL = 16;              // lanes that split k
   constexpr int CG = 32 / KL;         // lanes that split the warp's columns
   constexpr int KPG = D / KL;         // k values per lane
   constexpr int KQ = KPG / 4;         // float4 groups per lane
@@ -107,7 +109,7 @@ bigru_kernel(BiGruArgs a) {
   constexpr int CPL1 = NC1 / CG;      // gate columns per lane
   constexpr int CPL2 = NC2 / CG;      // candidate columns per lane
   static_assert(D % (CS * NWARP) == 0 && D % (4 * KL) == 0, "unsupported D / cluster size");
-  static_assert(NC2 % CG == 0 && CPL2 == 1, "one candidate column per lane");
+  static_assert(NC2 % CG == 0 && CPL2 == 2 && CPL1 == 4, "lane roles below assume 4 gate / 2 candidate columns per lane");
   static_assert(KPG <= 32 && 32 % KPG == 0, "a lane's k range sits inside one 32-unit chunk");
   constexpr int N1 = RB * CPL1, N2 = RB * CPL2;        // per-lane partial sums of the two phases
   constexpr uint32_t FULL_BYTES = RB * D * sizeof(float);
@@ -121,7 +123,7 @@ bigru_kernel(BiGruArgs a) {
   // state_to_state slice: [warp][q][lane][4 k] so a lane fetches four k of its column as one
   // vector; read in the candidate loop (the gate slice lives in registers for the whole sequence)
   extern __shared__ __align__(16) float w2s_dyn[];
-  float (*w2s)[KQ][32][4] = reinterpret_cast<float (*)[KQ][32][4]>(w2s_dyn);
+  float (*w2s)[KQ][CPL2][32][4] = reinterpret_cast<float (*)[KQ][CPL2][32][4]>(w2s_dyn);
   __shared__ __align__(8) unsigned long long mbar[2];   // [0]: h arrivals, [1]: h*r arrivals
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -156,34 +158,35 @@ bigru_kernel(BiGruArgs a) {
 #pragma unroll
   for (int q = 0; q < KQ; ++q)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w2s[warp][q][lane][i] = Ws[(long long)(kg * KPG + q * 4 + i) * D + u_warp + cg];
+    for (int c2 = 0; c2 < CPL2; ++c2)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w2s[warp][q][c2][lane][i] = Ws[(long long)(kg * KPG + q * 4 + i) * D + u_warp + cg * CPL2 + c2];
 
   for (int i = tid; i < RB * D; i += NWARP * 32) {
     const int r = i / D, u = i % D;
     hbuf[u / CH][r * CH + u % CH] = h0[u];
   }
 
-  // Lane roles after the reduce-scatters over the kg lanes (kg = lane >> 2, cg = lane & 3):
-  //   gate sum      (row1 = kg >> 1, column cl1 = cg * 2 + (kg & 1)): cl1 < NC2 update gate of unit cl1,
-  //                                                                  else reset gate of unit cl1 - NC2
-  //   candidate sum (row2 = kg >> 1, unit cg), duplicated in the lane pair kg, kg ^ 1
-  // h of (row, unit) lives in a register of lane 8 * row + unit (and its duplicate); everything
-  // the epilogues need from other lanes comes by shuffle, nothing goes through shared memory.
-  static_assert(RB == 4 && NC2 == 4 && CPL1 == 2, "lane roles below assume 4 rows x 4 units per warp");
-  const int row1 = kg >> 1, cl1 = cg * CPL1 + (kg & 1);
-  const bool is_z = cl1 < NC2;
-  const int unit1 = is_z ? cl1 : cl1 - NC2;
-  const int row2 = kg >> 1, unit2 = cg;
-  const int src_hold = 8 * row1 + unit1;                                  // h of my reset gate's unit
-  const int src_z = (2 * row2 + (unit2 & 1)) * 4 + (unit2 >> 1);           // update gate of my candidate's unit
+  // Lane roles after the reduce-scatters over the kg lanes (kg = lane >> 1, cg = lane & 1):
+  //   gate sum      (row1 = kg >> 2, unit1 = kg & 3): update gate on cg 0 lanes, reset gate on cg 1 lanes
+  //   candidate sum (row2 = kg >> 2, unit2 = cg * 2 + ((kg >> 1) & 1)), duplicated in the lane pair kg, kg ^ 1
+  // h of (row, unit) lives in a register of lane 8 * row + 4 * (unit & 1) + (unit >> 1) (and its
+  // duplicate); everything the epilogues need from other lanes comes by shuffle.
+  static_assert(RB == 4 && NC2 == 4, "lane roles below assume 4 rows x 4 units per warp");
+  const int row1 = kg >> 2, unit1 = kg & 3;
+  const bool is_z = cg == 0;
+  const int row2 = kg >> 2, unit2 = cg * 2 + ((kg >> 1) & 1);
+  const int src_hold = 8 * row1 + 4 * (unit1 & 1) + (unit1 >> 1);          // h of my reset gate's unit
+  const int src_z = (row2 * 4 + unit2) * 2;                                // update gate of my candidate's unit
   // sender role: lane = rowg * 8 + peer ships row rowg of this warp's 4 units to CTA `peer`
   const int rowg = lane >> 3, peer = lane & 7;
   const bool sender = peer < CS;
   int src_hr[4], src_h[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    src_hr[u] = (2 * rowg + (u & 1)) * 4 + 2 + (u >> 1);
-    src_h[u] = 8 * rowg + u;
+    src_hr[u] = (rowg * 4 + u) * 2 + 1;
+    src_h[u] = 8 * rowg + 4 * (u & 1) + (u >> 1);
   }
   const uint32_t bar_h = smem_u32(&mbar[0]), bar_hr = smem_u32(&mbar[1]);
   // where this warp's 4 units of row rowg land in the receiver
@@ -295,14 +298,19 @@ bigru_kernel(BiGruArgs a) {
       for (int i = 0; i < N2; ++i) ap[i] = 0ull;
 #pragma unroll
       for (int q = 0; q < KQ; ++q) {
-        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(&w2s[warp][q][lane][0]);
+        ulonglong2 w[CPL2];
+#pragma unroll
+        for (int c2 = 0; c2 < CPL2; ++c2) w[c2] = *reinterpret_cast<const ulonglong2*>(&w2s[warp][q][c2][lane][0]);
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
           const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&hrbuf[kpeer][r * CH + koff + q * 4]);
-          unsigned long long sacc = ap[r];
-          sacc = ffma2(v.x, w.x, sacc);
-          sacc = ffma2(v.y, w.y, sacc);
-          ap[r] = sacc;
+#pragma unroll
+          for (int c2 = 0; c2 < CPL2; ++c2) {
+            unsigned long long sacc = ap[r * CPL2 + c2];
+            sacc = ffma2(v.x, w[c2].x, sacc);
+            sacc = ffma2(v.y, w[c2].y, sacc);
+            ap[r * CPL2 + c2] = sacc;
+          }
         }
       }
 #pragma unroll
@@ -344,7 +352,7 @@ bigru_kernel(BiGruArgs a) {
 
 template <int D, int CS, int NWARP>
 int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
-  constexpr size_t W2S_BYTES = (size_t)NWARP * (D / 8 / 4) * 32 * 4 * sizeof(float);
+  constexpr size_t W2S_BYTES = (size_t)NWARP * (D / 16 / 4) * 2 * 32 * 4 * sizeof(float);
   static bool configured = false;
   if (!configured) {
     LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_kernel<D, CS, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -400,7 +408,7 @@ int bigru_sm_count() {
 int wide_clusters_resident() {
   static int n = -1;
   if (n < 0) {
-    constexpr size_t W2S_BYTES = (size_t)16 * (256 / 8 / 4) * 32 * 4 * sizeof(float);
+    constexpr size_t W2S_BYTES = (size_t)16 * (256 / 16 / 4) * 2 * 32 * 4 * sizeof(float);
     cudaFuncSetAttribute(bigru_kernel<256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2S_BYTES);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(4 * 64);
