@@ -323,6 +323,17 @@ def main():
         k_us = att["ms"] * 1e3 / max(1, att["launches"])
         dec_us = (prof["attention"]["ms"] + prof["window"]["ms"] + prof["dense"]["ms"]) * 1e3 / max(1, att["launches"])
     achieved = launch_bytes / (k_us * 1e-6) / 1e9 if k_us > 0 else 0.0
+    # the encoder recurrence has no bandwidth or tensor roofline: report time per
+    # sequential step next to the fp32 FMA time of its two dependent products
+    enc_steps, t_l = 0, W["T"]
+    for k in NET["subsample"]:
+        enc_steps += t_l
+        t_l = -(-t_l // k)
+    D = NET["dims_bidir"][0]
+    fma_per_step = 2 * W["B"] * 3 * D * D
+    recurrence = {"kernel": "bigru_kernel", "sequential_steps": enc_steps,
+                  "us_per_step": prof["bigru"]["ms"] * 1e3 / enc_steps if enc_steps else None,
+                  "fp32_fma_floor_us": fma_per_step / (148 * 128 * 1.965e9) * 1e6}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -338,7 +349,8 @@ def main():
                      "algorithmic_bytes_per_launch": launch_bytes, "us_per_launch": k_us,
                      "decoder_step_us": dec_us,
                      "decoder_step_frac": (step_bytes / (dec_us * 1e-6) / 1e9 / peaks["hbm_gbs"]) if dec_us > 0 else 0.0,
-                     "how": "CUDA events around every launch of the class in a separate profiled pass"},
+                     "how": "CUDA events around every launch of the class in a separate profiled pass",
+                     "encoder_recurrence": recurrence},
         "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "kernel_launches_per_step": {k: v["launches"] for k, v in prof.items()},
     }
