@@ -67,35 +67,6 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 
-// ---- point-to-point synchronisation between co-resident CTAs ----------------------------
-// A producer publishes a monotonically increasing counter with a release store after its CTA
-// barrier (release is cumulative over bar.sync, so every thread's prior global writes are
-// covered); a consumer's warp 0 polls the counters it depends on with acquire loads, then the
-// CTA barrier extends the ordering to all its threads.  Data itself is read with ld.global.cg.
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void flag_arrive(unsigned* flag, unsigned value) {
-  __syncthreads();
-  if (threadIdx.x == 0) st_release_gpu(flag, value);
-}
-__device__ __forceinline__ void flags_wait(const unsigned* flags, int n, unsigned value) {
-  if (threadIdx.x < 32) {
-    for (int j = threadIdx.x; j < n; j += 32) {
-      unsigned spins = 0;
-      while (ld_acquire_gpu(flags + j) < value) {
-        if (++spins > (1u << 22)) __trap();     // a lost producer must fail the launch, not hang the GPU
-      }
-    }
-  }
-  __syncthreads();
-}
-
 // ---- data-flow synchronisation: the data IS the flag ----------------------------------------
 // Buffers that carry values between CTAs of a persistent kernel are pre-filled with a sentinel
 // bit pattern (all ones: a NaN no arithmetic produces) and are written exactly once per element.
@@ -103,7 +74,6 @@ __device__ __forceinline__ void flags_wait(const unsigned* flags, int n, unsigne
 // load on the critical path instead of store -> fence -> flag -> poll -> load.
 constexpr unsigned LVSR_SENTINEL = 0xFFFFFFFFu;
 constexpr unsigned LVSR_SPIN_LIMIT = 1u << 22;
-static __constant__ unsigned g_flow_backoff_ns = 0;   // per translation unit; set by the launcher
 static __constant__ unsigned g_flow_spin_limit = LVSR_SPIN_LIMIT;
 __device__ __forceinline__ void st_flow_f32(float* p, float v) {
   asm volatile("st.relaxed.gpu.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
@@ -114,7 +84,6 @@ __device__ __forceinline__ float ld_flow_f32(const float* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     if (v != LVSR_SENTINEL) break;
     if (++spins > g_flow_spin_limit) __trap();     // a value that never arrives must fail the launch, not hang
-    if (g_flow_backoff_ns) __nanosleep(g_flow_backoff_ns);
   }
   return __uint_as_float(v);
 }
@@ -141,7 +110,6 @@ __device__ __forceinline__ float4 ld_flow_f4(const float* p) {
                  : "memory");
     if (x != LVSR_SENTINEL && y != LVSR_SENTINEL && z != LVSR_SENTINEL && w != LVSR_SENTINEL) break;
     if (++spins > g_flow_spin_limit) __trap();
-    if (g_flow_backoff_ns) __nanosleep(g_flow_backoff_ns);
   }
   return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
 }

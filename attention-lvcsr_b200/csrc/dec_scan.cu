@@ -10,9 +10,15 @@
 //   * phase A (attention) is row-parallel: a cluster of `cs` CTAs per decoder row streams the
 //     row's P and H slices once and merges (max, sum, partial context) through DSMEM.
 //   * phases B1..B3 (gates, candidate, next query) are 2-D tiled skinny products:
-//     16-row x nc-column tiles, K split over the 16 warps of the CTA, fused GRU epilogues.
-//   * phases are separated by a grid barrier (one L2 atomic per CTA + acquire poll); the
-//     window statistics of the next step (mean / median position) ride on the attention
+//     16-row x nc-column tiles, K split over the 16 warps of the CTA, fused GRU epilogues.  A CTA's
+//     gate tile and candidate tile cover the same units of the same rows, so update gate,
+//     candidate input and the state never leave its shared memory.
+//   * the batch is cut into independent islands of <= 16 rows (rows' attention clusters own the
+//     island's dense tiles); there are NO barriers or flags between CTAs: every cross-CTA value
+//     (query, context, h*r, next state, alignment, position statistic) lives in a per-step
+//     buffer the host fills with 0xFF bytes and is polled by its consumers until it is no longer
+//     the sentinel (common.cuh: ld_flow / st_flow).  One store + one load per hand-over.
+//   * the window statistics of the next step (mean / median position) ride on the attention
 //     exchange, so the windowing priors need no extra pass and no host round trip.
 #include "attention_row.cuh"
 
@@ -444,7 +450,7 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       smem = derive(a, cs, G, false);
     }
     if (smem == 0) continue;
-    // every cluster must be co-resident (grid barrier): ask the driver how many fit.  GPCs of
+    // every cluster must be co-resident (consumers poll producers): ask the driver how many fit.  GPCs of
     // 16-20 SMs hold only two 8-CTA clusters each, so large clusters cannot cover all SMs.
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
@@ -477,9 +483,6 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
     if (R * cs > G) continue;        // not enough clusters for one per row: try a smaller cluster
     cfg.numAttrs = 2;
     {
-      const char* bo = getenv("LVSR_FLOW_BACKOFF_NS");
-      const unsigned ns = bo ? (unsigned)atoi(bo) : 0u;
-      LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_backoff_ns, &ns, sizeof(ns), 0, cudaMemcpyHostToDevice, stream));
       // profilers slow the kernel down by orders of magnitude: let them raise the hang guard
       const char* sl = getenv("LVSR_FLOW_SPIN_LIMIT");
       const unsigned lim = sl ? (unsigned)strtoul(sl, nullptr, 10) : LVSR_SPIN_LIMIT;
