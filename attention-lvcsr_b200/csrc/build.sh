@@ -12,5 +12,5 @@ for f in gemm gemm_tc bigru attention decoder dec_scan api; do
   fi
   OBJS+=("$f.o")
 done
-$NVCC -shared -o liblvsr_b200.so "${OBJS[@]}" -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o liblvsr_b200.so "${OBJS[@]}" -lcudart
 echo "built $(pwd)/liblvsr_b200.so"
