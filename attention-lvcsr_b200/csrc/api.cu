@@ -705,14 +705,14 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     LVSR_CUDA_OK(cudaMemsetAsync(ctx_all, 0xFF, (size_t)L * B * E * sizeof(float), st));
     const bool trace = getenv("LVSR_DEC_TRACE") != nullptr;
     if (trace) {
-      d.trace = reinterpret_cast<unsigned long long*>(ws.i64((size_t)2 * L * 9 + (size_t)L * 8));
-      LVSR_CUDA_OK(cudaMemsetAsync(d.trace, 0, ((size_t)2 * L * 9 + (size_t)L * 8) * 8, st));
+      d.trace = reinterpret_cast<unsigned long long*>(ws.i64((size_t)2 * L * 9 + (size_t)L * 12 + (size_t)L * B));
+      LVSR_CUDA_OK(cudaMemsetAsync(d.trace, 0, ((size_t)2 * L * 9 + (size_t)L * 12 + (size_t)L * B) * 8, st));
     }
     int supported = 0;
     if (int rc = dec_scan_try(d, &supported, st)) return rc;
     scanned = supported != 0;
     if (trace && scanned) {
-      std::vector<unsigned long long> h((size_t)2 * L * 9 + (size_t)L * 8);
+      std::vector<unsigned long long> h((size_t)2 * L * 9 + (size_t)L * 12 + (size_t)L * B);
       LVSR_CUDA_OK(cudaMemcpyAsync(h.data(), d.trace, h.size() * 8, cudaMemcpyDeviceToHost, st));
       LVSR_CUDA_OK(cudaStreamSynchronize(st));
       const char* names[8] = {"A", "syncA", "B1", "sync1", "B2", "sync2", "B3", "sync3"};
@@ -735,6 +735,33 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
         fprintf(stderr, "[dec_scan trace] attention row 0:");
         for (int j = 0; j < 7; ++j) fprintf(stderr, " %s=%.2fus", an[j], n ? sum[j] / n * 1e-3 : 0.0);
         fprintf(stderr, "\n");
+      }
+      {
+        // gate tile of CTA 0: start of B1 -> x arrived -> products done -> cross-warp sums done -> end of B1
+        double sum[4] = {0};
+        int n = 0;
+        for (int i = 1; i + 1 < L; ++i, ++n) {
+          const unsigned long long* b = &h[(size_t)0 * L * 9 + (size_t)i * 9];
+          const unsigned long long* t = &h[(size_t)2 * L * 9 + (size_t)L * 8 + (size_t)i * 4];
+          sum[0] += (double)(t[0] - b[2]); sum[1] += (double)(t[1] - t[0]);
+          sum[2] += (double)(t[2] - t[1]); sum[3] += (double)(b[3] - t[2]);
+        }
+        {
+          // when each row's attention phase ended, relative to row 0 (mean over steps)
+          fprintf(stderr, "[dec_scan trace] end of attention vs row 0 (us):");
+          for (int r = 0; r < B; ++r) {
+            double acc = 0;
+            for (int i = 1; i + 1 < L; ++i) {
+              const unsigned long long* e = &h[(size_t)2 * L * 9 + (size_t)L * 12 + (size_t)i * B];
+              acc += (double)((long long)e[r] - (long long)e[0]);
+            }
+            fprintf(stderr, " %.1f", acc / (L - 2) * 1e-3);
+          }
+          fprintf(stderr, "\n");
+        }
+        fprintf(stderr, "[dec_scan trace] gate tile: wait_x=%.2fus products=%.2fus sums=%.2fus epilogue=%.2fus\n",
+                n ? sum[0] / n * 1e-3 : 0.0, n ? sum[1] / n * 1e-3 : 0.0, n ? sum[2] / n * 1e-3 : 0.0,
+                n ? sum[3] / n * 1e-3 : 0.0);
       }
     }
   }

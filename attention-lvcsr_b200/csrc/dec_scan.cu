@@ -52,6 +52,7 @@ struct DenseIO {
   int ncu;                      // units per tile (EP_GATES / EP_CAND)
   const float* rmask;           // [R] or null
   float* out;                   // EP_CAND: next state [R, C]; EP_QUERY: q [R, N]
+  unsigned long long* tr;       // LVSR_DEC_TRACE: [x arrived, products done, cross-warp sums done] or null
 };
 
 // One 16-row x (8*NQ)-column tile.  lane = ks*16 + rq*2 + cq: rows {2rq, 2rq+1}, columns
@@ -77,13 +78,20 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
   static_assert(DS_ROWS * NC <= DS_THREADS, "one output per thread");
   float ep_pref = 0.f;
   {
+    // volatile asm keeps the two dependent loads here, in front of the polling loads (plain loads
+    // may be sunk to their use at the end of the phase, where they would be exposed)
     const int rl = tid / NC, cl = tid % NC, r = r0 + rl;
     if (tid < DS_ROWS * NC && r < d.R) {
       if (d.mode == EP_GATES) {
         const int ncu = d.ncu, gate = cl / ncu, u = c0 + (cl - gate * ncu);
-        if (gate < 3 && u < d.C) ep_pref = __ldg(d.add + d.arow[r] * 3 * d.C + gate * d.C + u);
+        if (gate < 3 && u < d.C) {
+          long long lab;
+          asm volatile("ld.global.nc.s64 %0, [%1];\n" : "=l"(lab) : "l"(d.arow + r));
+          asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(ep_pref) : "l"(d.add + lab * 3 * d.C + gate * d.C + u));
+        }
       } else if (d.mode == EP_CAND) {
-        ep_pref = d.rmask ? __ldg(d.rmask + r) : 1.f;
+        ep_pref = 1.f;
+        if (d.rmask) asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(ep_pref) : "l"(d.rmask + r));
       }
     }
   }
@@ -110,6 +118,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       }
     }
   }
+  if (d.tr && tid == 0) d.tr[0] = global_ns();
 #pragma unroll
   for (int kb = 0; kb < KPER / 4; ++kb) {
 #pragma unroll
@@ -130,6 +139,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       }
     }
   }
+  if (d.tr && tid == 0) d.tr[1] = global_ns();
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -139,6 +149,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
       if (ks == 0) red[(size_t)warp * (DS_ROWS * NC) + (rq * 2 + i) * NC + cq * NCL + j] = v;
     }
   __syncthreads();
+  if (d.tr && tid == 0) d.tr[2] = global_ns();
   const int C = d.C;
   for (int o = tid; o < DS_ROWS * NC; o += DS_THREADS) {     // at most one iteration
     const int rl = o / NC, cl = o % NC;
@@ -344,6 +355,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       attention_row(io, att, a.tc_cap, rank, cs, true, true, false);
     }
     DS_STAMP(1);
+    if (a.trace && rank == 0 && tid == 0 && cluster_id < R)
+      a.trace[(size_t)2 * a.L * 9 + (size_t)a.L * 12 + (size_t)i * R + cluster_id] = global_ns();
     DS_STAMP(2);
 
     // ================= phase B1: gates + candidate inputs ==============================
@@ -351,6 +364,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       DenseIO d = {};
       d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = Rlim; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
       d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.hr = hr_cur; d.loc = loc; d.ncu = a.nc2;
+      d.tr = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)a.L * 8 + (size_t)i * 4 : nullptr;
       dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cgi * a.nc2, red);
     }
     DS_STAMP(3);
