@@ -305,27 +305,30 @@ def _gru_params(params, base):
                 initial_state=params[base + ".initial_state"])
 
 
-def recurrent_with_fork(x, mask, params, base, reverse):
-    """lvsr/bricks/__init__.py:39-43: Fork(Linear) over the WHOLE sequence, then the scan."""
+def recurrent_with_fork(x, mask, params, base, reverse, activation=np.tanh, gate_activation=sigmoid):
+    """lvsr/bricks/__init__.py:39-43: Fork(Linear) over the WHOLE sequence, then the scan.
+    (The activations are arguments only so the reference's Tanh-gated known-answer test can be
+    driven through this very function; the recognizer always uses tanh / logistic.)"""
     a = linear(x, params[base + "/fork/fork_inputs.W"], params[base + "/fork/fork_inputs.b"])
     g = linear(x, params[base + "/fork/fork_gate_inputs.W"], params[base + "/fork/fork_gate_inputs.b"])
-    return gru_scan(a, g, mask, _gru_params(params, base + "/gatedrecurrent"), reverse=reverse)
+    return gru_scan(a, g, mask, _gru_params(params, base + "/gatedrecurrent"), reverse=reverse,
+                    activation=activation, gate_activation=gate_activation)
 
 
-def bidirectional(x, mask, params, base):
+def bidirectional(x, mask, params, base, **act):
     """B/bricks/recurrent.py:655-663: forward scan; backward scan with
     reverse=True then [::-1]; concatenate on the feature axis, forward first."""
-    fwd = recurrent_with_fork(x, mask, params, base + "/forward", reverse=False)
-    bwd = recurrent_with_fork(x, mask, params, base + "/backward", reverse=True)[::-1]
+    fwd = recurrent_with_fork(x, mask, params, base + "/forward", reverse=False, **act)
+    bwd = recurrent_with_fork(x, mask, params, base + "/backward", reverse=True, **act)[::-1]
     return np.concatenate([fwd, bwd], axis=2)
 
 
-def encoder(cfg, params, x, mask=None, return_layers=False):
+def encoder(cfg, params, x, mask=None, return_layers=False, **act):
     """lvsr/bricks/__init__.py:71-78.  x [T,B,F], mask [T,B] -> (encoded [T',B,E],
     encoded_mask [T',B]).  Subsampling x[::k] happens AFTER the full-rate layer."""
     layers = []
     for l, k in enumerate(cfg["subsample"]):
-        x = bidirectional(x, mask, params, "/recognizer/encoder/bidir%d" % l)
+        x = bidirectional(x, mask, params, "/recognizer/encoder/bidir%d" % l, **act)
         x = x[::k]
         if mask is not None:
             mask = mask[::k]
