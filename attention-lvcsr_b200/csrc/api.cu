@@ -128,6 +128,7 @@ using namespace lvsr;
 
 struct lvsr_model {
   lvsr_config cfg;
+  int device = 0;                   // the GPU this handle lives on (current device at lvsr_model_create)
   int E;
   std::vector<Param> params;
   std::map<std::string, int> index;
@@ -143,6 +144,9 @@ struct lvsr_model {
   float *Wp_hi = nullptr, *Wp_lo = nullptr;
   bool use_tc = true;
   float v_bias = 0.f;               // host copy of energy_comp/linear.b
+  unsigned* status = nullptr;       // device word: launch status of the data-flow decoder (common.cuh LVSR_FLOW_*)
+  bool force_stepwise = false;      // set while a failed persistent launch is re-run on the step-wise kernels
+  long long dec_fallbacks = 0;      // how often that happened
   bool finalized = false;
   Arena ws;
 
@@ -342,6 +346,21 @@ size_t cost_ws_bytes(const lvsr_model* m, int Tp, int B, int L) {
   return f * sizeof(float) + (1 << 16);
 }
 
+// Every entry point runs on the handle's own GPU, whatever device the calling thread has current
+// (a handle is bound to the device that was current at lvsr_model_create).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const lvsr_model* m) {
+    if (!m) return;
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != m->device) {
+      prev = cur;
+      cudaSetDevice(m->device);
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct ArenaScope {
   lvsr_model* m;
   cudaStream_t st;
@@ -403,13 +422,16 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
              "bad post_merge_activation");
   LVSR_CHECK(cfg->post_merge_activation == LVSR_ACT_MAXOUT || cfg->maxout_pieces == 1,
              "maxout_pieces must be 1 unless the activation is Maxout");
-  LVSR_CHECK(cfg->conv_num_filters >= 1 && cfg->conv_num_filters <= 16 && cfg->conv_n >= 0, "bad conv config");
+  LVSR_CHECK(cfg->conv_num_filters >= 1 && cfg->conv_num_filters <= 16, "conv_num_filters %d not in [1,16]", cfg->conv_num_filters);
+  // the centre crop [:, :, n:-n] of the reference is EMPTY for n = 0 (lvsr/bricks/attention.py:109-110)
+  LVSR_CHECK(cfg->conv_n >= 1, "conv_n must be >= 1 (got %d)", cfg->conv_n);
   LVSR_CHECK(cfg->num_phonemes >= 1 && cfg->num_phonemes <= 128, "num_phonemes out of range");
   int dev_count = 0;
   LVSR_CUDA_OK(cudaGetDeviceCount(&dev_count));
   LVSR_CHECK(dev_count > 0, "no CUDA device: the B200 path has no CPU fallback");
   lvsr_model* m = new lvsr_model();
   m->cfg = *cfg;
+  LVSR_CUDA_OK(cudaGetDevice(&m->device));
   m->E = 2 * cfg->dims_bidir[cfg->num_layers - 1];
   build_param_table(m);
   for (auto& p : m->params) {
@@ -421,12 +443,18 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
     }
     cudaMemset(p.dev, 0, (size_t)p.count * sizeof(float));
   }
+  if (cudaMalloc(reinterpret_cast<void**>(&m->status), 64) != cudaSuccess) {
+    lvsr_model_destroy(m);
+    return set_error("cudaMalloc(status) failed");
+  }
+  cudaMemset(m->status, 0, 64);
   *out = m;
   return 0;
 }
 
 int lvsr_model_destroy(lvsr_model* m) {
   if (!m) return 0;
+  DeviceGuard device_guard(m);
   cudaDeviceSynchronize();
   for (auto& p : m->params) if (p.dev) cudaFree(p.dev);
   for (float* p : m->Wcat) if (p) cudaFree(p);
@@ -440,8 +468,19 @@ int lvsr_model_destroy(lvsr_model* m) {
   if (m->Wff_cat) cudaFree(m->Wff_cat);
   if (m->bff_cat) cudaFree(m->bff_cat);
   if (m->FF) cudaFree(m->FF);
+  if (m->status) cudaFree(m->status);
   m->ws.destroy();
   delete m;
+  return 0;
+}
+
+int lvsr_model_status(lvsr_model* m, int32_t* launch_status, int64_t* stepwise_fallbacks) {
+  DeviceGuard device_guard(m);
+  LVSR_CHECK(m && launch_status, "null argument");
+  unsigned hst = 0;
+  LVSR_CUDA_OK(cudaMemcpy(&hst, m->status, sizeof(hst), cudaMemcpyDeviceToHost));   // synchronises with the device
+  *launch_status = (int32_t)hst;
+  if (stepwise_fallbacks) *stepwise_fallbacks = m->dec_fallbacks;
   return 0;
 }
 
@@ -458,6 +497,7 @@ int lvsr_model_param_shape(const lvsr_model* m, int i, int64_t shape[2], int32_t
   return 0;
 }
 int lvsr_model_set_param(lvsr_model* m, const char* name, const float* host, int64_t count) {
+  DeviceGuard device_guard(m);
   LVSR_CHECK(m && name && host, "null argument");
   auto it = m->index.find(name);
   LVSR_CHECK(it != m->index.end(), "unknown parameter '%s'", name);
@@ -468,6 +508,7 @@ int lvsr_model_set_param(lvsr_model* m, const char* name, const float* host, int
   return 0;
 }
 int lvsr_model_get_param(const lvsr_model* m, const char* name, float* host, int64_t count) {
+  DeviceGuard device_guard(m);
   LVSR_CHECK(m && name && host, "null argument");
   auto it = m->index.find(name);
   LVSR_CHECK(it != m->index.end(), "unknown parameter '%s'", name);
@@ -478,6 +519,7 @@ int lvsr_model_get_param(const lvsr_model* m, const char* name, float* host, int
 }
 
 int lvsr_model_finalize(lvsr_model* m) {
+  DeviceGuard device_guard(m);
   LVSR_CHECK(m, "null model");
   const lvsr_config& c = m->cfg;
   cudaStream_t st = 0;
@@ -579,6 +621,7 @@ int lvsr_encoded_dim(const lvsr_model* m) { return m ? m->E : 0; }
 
 int lvsr_encoder_forward(lvsr_model* m, const float* x, const float* mask, int32_t T, int32_t B,
                          float* attended, float* attended_mask, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(x && attended && attended_mask && T > 0 && B > 0, "encoder_forward: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -626,6 +669,7 @@ int lvsr_encoder_forward(lvsr_model* m, const float* x, const float* mask, int32
 }
 
 int lvsr_preprocess(lvsr_model* m, const float* attended, int32_t Tp, int32_t U, float* out, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && out && Tp > 0 && U > 0, "preprocess: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -645,6 +689,7 @@ int lvsr_preprocess(lvsr_model* m, const float* attended, int32_t Tp, int32_t U,
 int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended_mask, int32_t Tp, int32_t B,
                      const int64_t* labels, const float* labels_mask, int32_t L, float* costs,
                      float* weights_out, float* energies_out, float* states_out, float* wavg_out, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && attended_mask && labels && costs && Tp > 0 && B > 0 && L > 0, "cost_matrix: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -671,7 +716,8 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
   if (int rc = fill_f32(costs, (long long)L * B, 0.f, st)) return rc;
 
   bool scanned = false;
-  if (getenv("LVSR_NO_DEC_SCAN") == nullptr) {
+  LVSR_CUDA_OK(cudaMemsetAsync(m->status, 0, sizeof(unsigned), st));
+  if (getenv("LVSR_NO_DEC_SCAN") == nullptr && !m->force_stepwise) {
     DecScanArgs d = {};
     d.P = P; d.H = attended; d.maskH = attended_mask;
     d.filt = m->P(std::string(ATT) + "/conv1d.filters");
@@ -686,6 +732,7 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     d.labels = lab; d.lmask = labels_mask;
     d.s_all = s_all; d.ctx_all = ctx_all; d.w0 = w0;
     d.e_seq = energies_out; d.e_scratch = e_scratch;
+    d.status = m->status;
     d.Tp = Tp; d.B = B; d.L = L; d.M = M; d.E = E; d.C = C; d.K = c.conv_num_filters; d.n = c.conv_n;
     d.normalizer = c.energy_normalizer;
     // per-step hand-over buffers of the data-flow decoder; everything another CTA polls starts
@@ -711,6 +758,25 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     int supported = 0;
     if (int rc = dec_scan_try(d, &supported, st)) return rc;
     scanned = supported != 0;
+    if (scanned && getenv("LVSR_DEC_CHECK") != nullptr) {
+      // debug post-condition: the launch reported success and every hand-over word was written
+      LVSR_CUDA_OK(cudaStreamSynchronize(st));
+      unsigned hst = 0;
+      LVSR_CUDA_OK(cudaMemcpy(&hst, m->status, sizeof(hst), cudaMemcpyDeviceToHost));
+      LVSR_CHECK(hst == 0, "LVSR_DEC_CHECK: persistent decoder launch status %u (2 = a value never arrived, "
+                 "3 = launched without its cluster shape)", hst);
+      struct { const char* name; const float* p; size_t n; } bufs[] = {
+          {"weights", d.w_all, (size_t)L * B * Tp}, {"queries", d.q_all, (size_t)L * B * M},
+          {"reset-gated states", d.hr_all, (size_t)L * B * C}, {"states", s_all, (size_t)(L + 1) * B * C},
+          {"weighted averages", ctx_all, (size_t)L * B * E},
+          {"row positions", d.rowpos_all, c.prior_type == LVSR_PRIOR_EXPANDING ? (size_t)B : (size_t)(L + 1) * B}};
+      for (auto& b : bufs) {
+        long long left = 0;
+        if (int rc = count_sentinels(b.p, (long long)b.n, &left, st)) return rc;
+        // the query of step L is never needed; everything else must have been produced
+        LVSR_CHECK(left == 0, "LVSR_DEC_CHECK: %lld sentinel words left in the %s buffer", left, b.name);
+      }
+    }
     if (trace && scanned) {
       std::vector<unsigned long long> h((size_t)2 * L * 9 + (size_t)L * 12 + (size_t)L * B);
       LVSR_CUDA_OK(cudaMemcpyAsync(h.data(), d.trace, h.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -793,6 +859,7 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     if (int rc = gemm_bias(b, st)) return rc;
     ReadoutArgs r = readout_args(m, R, merged);
     r.labels = lab; r.lmask = labels_mask; r.costs_picked = costs;
+    r.poison = scanned ? m->status : nullptr;
     if (int rc = readout_costs(r, st)) return rc;
   }
   if (states_out)
@@ -802,6 +869,7 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
 
 int lvsr_initial_states(lvsr_model* m, int32_t Tp, int32_t R, float* states, int64_t* outputs, float* wavg,
                         float* weights, float* energies, int64_t* step, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(states && outputs && wavg && weights && energies && step && Tp > 0 && R > 0, "initial_states: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -817,6 +885,7 @@ int lvsr_initial_states(lvsr_model* m, int32_t Tp, int32_t R, float* states, int
 int lvsr_logprobs(lvsr_model* m, const float* attended, const float* preprocessed, const float* attended_mask,
                   int32_t Tp, int32_t U, const int32_t* row_utt, int32_t R, const float* states,
                   const float* weights, const int64_t* step, float* out, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && attended_mask && states && weights && step && out && Tp > 0 && U > 0 && R > 0,
              "logprobs: bad arguments");
@@ -849,6 +918,7 @@ int lvsr_next_states(lvsr_model* m, const float* attended, const float* preproce
                      int32_t Tp, int32_t U, const int32_t* row_utt, int32_t R, const float* states,
                      const float* weights, const int64_t* step, const int64_t* outputs, float* next_states,
                      float* next_wavg, float* next_weights, float* next_energies, int64_t* next_step, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && attended_mask && states && weights && step && outputs && next_states && next_wavg &&
                  next_weights && next_energies && next_step && Tp > 0 && U > 0 && R > 0,
@@ -873,6 +943,7 @@ int lvsr_next_states(lvsr_model* m, const float* attended, const float* preproce
 
 int lvsr_recognizer_cost_host(lvsr_model* m, const float* x_h, const float* mask_h, const int64_t* labels_h,
                               const float* lmask_h, int32_t T, int32_t B, int32_t L, float* costs_h, void* stream) {
+  DeviceGuard device_guard(m);
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(x_h && labels_h && costs_h && T > 0 && B > 0 && L > 0, "recognizer_cost_host: bad arguments");
   for (long long i = 0; i < (long long)L * B; ++i)       // host memory: the lookup's IndexError, up front
@@ -904,8 +975,23 @@ int lvsr_recognizer_cost_host(lvsr_model* m, const float* x_h, const float* mask
     if (!rc) rc = lvsr_cost_matrix(m, att, attm, Tp, B, reinterpret_cast<const int64_t*>(lab), lmask, L, costs,
                                    nullptr, nullptr, nullptr, nullptr, stream);
     if (!rc) {
+      unsigned hst = 0;
       LVSR_CUDA_OK(cudaMemcpyAsync(costs_h, costs, (size_t)L * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LVSR_CUDA_OK(cudaMemcpyAsync(&hst, m->status, sizeof(hst), cudaMemcpyDeviceToHost, st));
       LVSR_CUDA_OK(cudaStreamSynchronize(st));
+      if (hst != 0) {
+        // the persistent decoder gave up (status in common.cuh): same math on the step-wise kernels
+        if (m->dec_fallbacks++ == 0)
+          fprintf(stderr, "[lvsr_b200] persistent decoder launch failed (status %u); re-running on the step-wise kernels\n", hst);
+        m->force_stepwise = true;
+        rc = lvsr_cost_matrix(m, att, attm, Tp, B, reinterpret_cast<const int64_t*>(lab), lmask, L, costs,
+                              nullptr, nullptr, nullptr, nullptr, stream);
+        m->force_stepwise = false;
+        if (!rc) {
+          LVSR_CUDA_OK(cudaMemcpyAsync(costs_h, costs, (size_t)L * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+          LVSR_CUDA_OK(cudaStreamSynchronize(st));
+        }
+      }
     }
   }
   return rc;

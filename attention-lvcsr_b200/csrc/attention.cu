@@ -123,25 +123,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) att_step_kernel(AttStepArgs a,
   attention_row(io, smem, tc_cap, rank, cs, false, false, true);
 }
 
-int g_num_sms = 0;
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+int num_sms() { return device_sm_count(); }
 
 int launch_att(const AttStepArgs& a, int cs, cudaStream_t stream) {
   const int tc_cap = ceil_div(a.Tp, cs);
   const size_t smem = att_smem_floats(a.M, a.E, a.K, a.n, tc_cap, cs) * sizeof(float);
   LVSR_CHECK(smem <= 227 * 1024, "attention_step: shared memory %zu B exceeds 227 KB (Tp=%d, cs=%d)", smem, a.Tp, cs);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[LVSR_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (smem > configured[dev]) {
     LVSR_CUDA_OK(cudaFuncSetAttribute(att_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured[dev] = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(a.R * cs);
@@ -172,7 +164,7 @@ int attention_window(const WindowArgs& a, cudaStream_t stream) {
 int attention_step(const AttStepArgs& a, cudaStream_t stream) {
   ProfScope prof("attention", stream);
   LVSR_CHECK(a.M == 128 || a.M == 256 || a.M == 512, "attention_step: dim_matcher %d unsupported (128, 256 or 512)", a.M);
-  LVSR_CHECK(a.E % 4 == 0, "attention_step: encoded dim must be a multiple of 4");
+  LVSR_CHECK(a.E % 4 == 0 && a.E <= 4 * ATT_NT, "attention_step: encoded dim must be a multiple of 4 and <= %d", 4 * ATT_NT);
   LVSR_CHECK(a.E / 4 <= ATT_THREADS, "attention_step: encoded dim %d > 1024 unsupported", a.E);
   LVSR_CHECK(a.K >= 1 && a.K <= 16, "attention_step: conv_num_filters %d not in [1,16]", a.K);
   if (a.R <= 0) return 0;

@@ -86,6 +86,25 @@ __device__ __forceinline__ unsigned long long att_global_ns() {
 }
 #define ATT_STAMP(j) do { if (a.trace && threadIdx.x == 0) a.trace[j] = att_global_ns(); } while (0)
 
+// -DLVSR_DEC_DEBUG: record the first NaN sightings (stage, step, CTA, thread, index) of a launch.
+#ifdef LVSR_DEC_DEBUG
+__device__ unsigned long long g_dbg_events[64];
+__device__ unsigned int g_dbg_count = 0;
+__device__ int g_dbg_step = 0;
+__device__ __forceinline__ void dbg_nan(int stage, float v, int idx) {
+  if (v != v) {
+    const unsigned k = atomicAdd(&g_dbg_count, 1u);
+    if (k < 64)
+      g_dbg_events[k] = ((unsigned long long)stage << 56) | ((unsigned long long)(g_dbg_step & 0xff) << 48) |
+                        ((unsigned long long)(blockIdx.x & 0xffff) << 32) | ((unsigned long long)(threadIdx.x & 0xffff) << 16) |
+                        (unsigned long long)(idx & 0xffff);
+  }
+}
+#define DBG_NAN(stage, v, idx) dbg_nan(stage, v, idx)
+#else
+#define DBG_NAN(stage, v, idx) do { } while (0)
+#endif
+
 struct AttSmem {
   float *sq, *sv, *sWh, *sfiltT, *salpha, *se, *su, *sblk, *sred, *xs, *xctx;
   uint32_t* sF;          // [(tc_cap+16)][16]: words 0..7 = hi pairs, 8..15 = lo pairs
@@ -190,9 +209,12 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
       float d[4];
       d[0] = pc[j][0].x + qq[j][0]; d[1] = pc[j][0].y + qq[j][1];
       d[2] = pc[j][1].x + qq[j][0]; d[3] = pc[j][1].y + qq[j][1];
+      DBG_NAN(4, pc[j][0].x + pc[j][0].y + pc[j][1].x + pc[j][1].y, tile * 16 + g);
+      DBG_NAN(5, qq[j][0] + qq[j][1], j);
       mma_bf16_16816(d, al, bh[j][0], bh[j][1]);     // small terms first
       mma_bf16_16816(d, ah, bl[j][0], bl[j][1]);
       mma_bf16_16816(d, ah, bh[j][0], bh[j][1]);
+      DBG_NAN(6, d[0] + d[1] + d[2] + d[3], tile * 16 + g);
       ea = fmaf(vv[j][0], fast_tanh(d[0]), ea);
       ea = fmaf(vv[j][1], fast_tanh(d[1]), ea);
       eb = fmaf(vv[j][0], fast_tanh(d[2]), eb);
@@ -200,6 +222,7 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
     }
     ea += __shfl_xor_sync(0xffffffffu, ea, 1); ea += __shfl_xor_sync(0xffffffffu, ea, 2);
     eb += __shfl_xor_sync(0xffffffffu, eb, 1); eb += __shfl_xor_sync(0xffffffffu, eb, 2);
+    DBG_NAN(7, ea + eb, tile * 16 + g);
     if (tig == 0) {
       part[ta] = ea;       // this warp's private partial sums; rows >= nt land in the 16-row padding
       part[tb] = eb;
@@ -207,6 +230,12 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
 #pragma unroll
     for (int j = 0; j < NTW; ++j) { pc[j][0] = pn[j][0]; pc[j][1] = pn[j][1]; }
   }
+}
+
+__device__ __forceinline__ float gmax_of(const float* xs, int cs) {
+  float g = -INFINITY;
+  for (int r = 0; r < cs; ++r) g = fmaxf(g, xs[r * 4 + 0]);
+  return g;
 }
 
 // ATT_NT threads.  `constants_staged`: a persistent caller already ran att_stage_constants.
@@ -238,6 +267,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       const int prel = t0 - n + i;            // window-relative position; zero padding is
       float val = 0.f;                        // relative to the CUT
       if (prel >= 0 && prel < Tw) val = flow ? ld_flow_f32(a.w_prev + b0 + prel) : a.w_prev[b0 + prel];
+      DBG_NAN(1, val, i);
       s.salpha[i] = val;
     }
   }
@@ -302,6 +332,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float x0 = (t < nt) ? acc[2 * c] : 0.f, x1 = (t < nt) ? acc[2 * c + 1] : 0.f;
+          DBG_NAN(2, x0 + x1, t);
           const float h0 = bf16_round(x0), h1 = bf16_round(x1);
           row[c] = pack_bf16(h0, h1);
           row[8 + c] = pack_bf16(x0 - h0, x1 - h1);
@@ -310,7 +341,10 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
     }
   }
   // the query is consumed only now: in flow mode its producers ran concurrently with the conv
-  for (int i = tid; i < M; i += NT) s.sq[i] = flow ? ld_flow_f32(a.q_row + i) : a.q_row[i];
+  for (int i = tid; i < M; i += NT) {
+    s.sq[i] = flow ? ld_flow_f32(a.q_row + i) : a.q_row[i];
+    DBG_NAN(3, s.sq[i], i);
+  }
   __syncthreads();
   ATT_STAMP(2);
 
@@ -326,6 +360,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
       float e = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) e += s.sred[(size_t)w * stride + t];
+      DBG_NAN(8, e, t);
       s.se[t] = e;
     }
   }
@@ -442,8 +477,14 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   ATT_STAMP(6);
 
   // ---- combine ---------------------------------------------------------------------
-  float gmax = -INFINITY;
-  for (int r = 0; r < cs; ++r) gmax = fmaxf(gmax, xs[r * 4 + 0]);
+  // Everything this step still needs from the exchange buffers is read into registers first; a CTA
+  // barrier then separates those reads from the stores that let other CTAs run ahead (a peer's NEXT
+  // exchange overwrites xs / xctx, and it can only get there through values stored below).
+  const float gmax = gmax_of(xs, cs);
+  auto scale_of = [&](int r) -> float {
+    if (a.normalizer != LVSR_NORM_SOFTMAX) return 1.f;
+    return (xs[r * 4 + 1] > 0.f) ? __expf(xs[r * 4 + 0] - gmax) : 0.f;
+  };
   float gsum = 0.f, gany = 0.f, myscale = 0.f;
   for (int r = 0; r < cs; ++r) {
     const float ls = xs[r * 4 + 1];
@@ -456,6 +497,44 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   }
   const float norm = gsum + (gany > 0.f ? 0.f : 1.f);     // +1 when no position has mask == 1, attention.py:211-212
   const float inv = 1.f / norm;
+
+  // position statistic of the new alignment (next step's window): who reports it is decided by ONE
+  // rule evaluated identically by every thread of every rank from the exchanged masses (same
+  // instruction sequence on the same xs values), so exactly one thread in the cluster writes
+  // rowpos_out for any input.
+  //   mean:   rank 0.
+  //   median: the first rank whose inclusive prefix of alignment mass reaches 0.5 and that owns at
+  //           least one position; rank 0 reports 0 when no prefix does (all positions masked:
+  //           cumsum never crosses, argmax of zeros = 0, attention.py:138-144).
+  float mean_pos = 0.f, owner_prefix = 0.f;
+  int owner = -1;
+  if (a.rowpos_out != nullptr) {
+    if (a.rowpos_mode == LVSR_PRIOR_WINDOW_MEAN) {
+      for (int r = 0; r < cs; ++r) mean_pos = fmaf(scale_of(r), xs[r * 4 + 3], mean_pos);
+      mean_pos *= inv;
+    } else {
+      float prefix = 0.f;
+      for (int r = 0; r < cs; ++r) {
+        const float mass = scale_of(r) * xs[r * 4 + 1] * inv;
+        const int nt_r = min(Tw, r * tc + tc) - min(Tw, r * tc);
+        if (owner < 0 && nt_r > 0 && prefix + mass >= 0.5f) { owner = r; owner_prefix = prefix; }
+        prefix += mass;
+      }
+    }
+  }
+  float ctx_reg[4] = {0.f, 0.f, 0.f, 0.f};     // E <= 4 * NT (checked by the planners)
+  if (rank == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * NT;
+      if (e < E) {
+        float acc = 0.f;
+        for (int r = 0; r < cs; ++r) acc = fmaf(scale_of(r), xctx[(size_t)r * E + e], acc);
+        ctx_reg[q] = acc * inv;
+      }
+    }
+  }
+  __syncthreads();
 
   for (int t = tid; t < nt; t += NT) {
     const float wv = s.su[t] * myscale * inv;
@@ -470,66 +549,45 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
     }
   }
   if (rank == 0) {
-    for (int e = tid; e < E; e += NT) {
-      float acc = 0.f;
-      for (int r = 0; r < cs; ++r) {
-        float sc = 1.f;
-        if (a.normalizer == LVSR_NORM_SOFTMAX) sc = (xs[r * 4 + 1] > 0.f) ? __expf(xs[r * 4 + 0] - gmax) : 0.f;
-        acc = fmaf(sc, xctx[(size_t)r * E + e], acc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * NT;
+      if (e < E) {
+        if (flow) st_flow_f32(a.ctx_out + e, ctx_reg[q]); else a.ctx_out[e] = ctx_reg[q];
       }
-      if (flow) st_flow_f32(a.ctx_out + e, acc * inv); else a.ctx_out[e] = acc * inv;
     }
   }
 
   ATT_STAMP(7);
-  // ---- position statistic of the new alignment (next step's window) --------------------
   if (a.rowpos_out != nullptr && warp == 0) {
-    auto scale_of = [&](int r) -> float {
-      if (a.normalizer != LVSR_NORM_SOFTMAX) return 1.f;
-      return (xs[r * 4 + 1] > 0.f) ? __expf(xs[r * 4 + 0] - gmax) : 0.f;
-    };
     if (a.rowpos_mode == LVSR_PRIOR_WINDOW_MEAN) {
-      if (rank == 0 && lane == 0) {
-        float pos = 0.f;
-        for (int r = 0; r < cs; ++r) pos = fmaf(scale_of(r), xs[r * 4 + 3], pos);
-        st_flow_f32(a.rowpos_out, pos * inv);
-      }
-    } else {
-      // median: first index j with cumsum(alpha) >= 0.5 -> j - 1 (0 when j == 0 or no crossing)
-      float prefix = 0.f, total = 0.f;
-      for (int r = 0; r < cs; ++r) {
-        const float mass = scale_of(r) * xs[r * 4 + 1] * inv;
-        if (r < rank) prefix += mass;
-        total += mass;
-      }
-      const float mine = myscale * lsum * inv;
-      const bool responsible = (prefix < 0.5f) && (prefix + mine >= 0.5f) && nt > 0;
-      if (responsible) {
-        const int chunk = (nt + 31) / 32;
-        const int i0 = min(nt, lane * chunk), i1 = min(nt, i0 + chunk);
-        const double sc = (double)(myscale * inv);
-        double part = 0.0;
-        for (int t = i0; t < i1; ++t) part += (double)s.su[t] * sc;
-        double incl = part;
+      if (rank == 0 && lane == 0) st_flow_f32(a.rowpos_out, mean_pos);
+    } else if (owner < 0) {
+      if (rank == 0 && lane == 0) st_flow_f32(a.rowpos_out, 0.f);
+    } else if (owner == rank) {
+      // median: first index j with cumsum(alpha) >= 0.5 -> j - 1 (0 when j == 0)
+      const int chunk = (nt + 31) / 32;
+      const int i0 = min(nt, lane * chunk), i1 = min(nt, i0 + chunk);
+      const double sc = (double)(myscale * inv);
+      double part = 0.0;
+      for (int t = i0; t < i1; ++t) part += (double)s.su[t] * sc;
+      double incl = part;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const double nb = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += nb;
-        }
-        double run = (double)prefix + (incl - part);
-        int cross = 0x7fffffff;
-        for (int t = i0; t < i1; ++t) {
-          run += (double)s.su[t] * sc;
-          if (run - 0.5 >= 0.0) { cross = t; break; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cross = min(cross, __shfl_xor_sync(0xffffffffu, cross, o));
-        if (cross == 0x7fffffff) cross = nt - 1;          // rounding at the chunk edge
-        const int j = b0 + t0 + cross;
-        if (lane == 0) st_flow_f32(a.rowpos_out, (j == 0) ? 0.f : (float)(j - 1));
-      } else if (rank == 0 && lane == 0 && !(total >= 0.5f)) {
-        st_flow_f32(a.rowpos_out, 0.f);
+      for (int o = 1; o < 32; o <<= 1) {
+        const double nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
       }
+      double run = (double)owner_prefix + (incl - part);
+      int cross = 0x7fffffff;
+      for (int t = i0; t < i1; ++t) {
+        run += (double)s.su[t] * sc;
+        if (run - 0.5 >= 0.0) { cross = t; break; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cross = min(cross, __shfl_xor_sync(0xffffffffu, cross, o));
+      if (cross == 0x7fffffff) cross = nt - 1;            // the fp32 prefix said "here", the fp64 rescan fell one ulp short
+      const int j = b0 + t0 + cross;
+      if (lane == 0) st_flow_f32(a.rowpos_out, (j == 0) ? 0.f : (float)(j - 1));
     }
   }
 }

@@ -353,11 +353,12 @@ bigru_kernel(BiGruArgs a) {
 template <int D, int CS, int NWARP>
 int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   constexpr size_t W2S_BYTES = (size_t)NWARP * (D / 16 / 4) * 2 * 32 * 4 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[LVSR_MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_kernel<D, CS, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)W2S_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   const int groups = ceil_div(a.B, RB);
   cudaLaunchConfig_t cfg = {};
@@ -392,22 +393,17 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-int bigru_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int bigru_sm_count() { return device_sm_count(); }
 
 // how many <256, 4, 16> clusters the device holds at once (a GPC takes floor(SMs / 4) of them; the
 // count differs between parts with different floor-sweeping, so ask the driver)
 int wide_clusters_resident() {
-  static int n = -1;
-  if (n < 0) {
+  static int per_dev[LVSR_MAX_DEVICES];
+  static bool known[LVSR_MAX_DEVICES] = {false};
+  const int dev = current_device();
+  int& n = per_dev[dev];
+  if (!known[dev]) {
+    known[dev] = true;
     constexpr size_t W2S_BYTES = (size_t)16 * (256 / 16 / 4) * 2 * 32 * 4 * sizeof(float);
     cudaFuncSetAttribute(bigru_kernel<256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2S_BYTES);
     cudaLaunchConfig_t cfg = {};

@@ -47,6 +47,24 @@ struct ProfScope {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (dynamic shared-memory opt-in), SM counts and occupancy answers are properties
+// of a DEVICE, not of the process: caches are keyed by the current device ordinal.
+constexpr int LVSR_MAX_DEVICES = 64;
+static inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < LVSR_MAX_DEVICES) ? dev : 0;
+}
+static inline int device_sm_count() {
+  static int sms[LVSR_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+
 // ---- device math: accurate enough for the 1e-4 gate against the float64 oracle ----
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
@@ -74,16 +92,35 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 // load on the critical path instead of store -> fence -> flag -> poll -> load.
 constexpr unsigned LVSR_SENTINEL = 0xFFFFFFFFu;
 constexpr unsigned LVSR_SPIN_LIMIT = 1u << 22;
+// Launch status word of a data-flow kernel (device memory, zeroed by the host before the launch):
+//   0 ok; LVSR_FLOW_TIMEOUT: a value never arrived (every poller gives up, the kernel runs to its
+//   end with meaningless data instead of trapping -- a trap would take the whole CUDA context and
+//   PyTorch with it); LVSR_FLOW_BAD_CLUSTER: the launch did not get the planned cluster shape.
+// The host reads it at its next synchronisation point and re-runs the call on the step-wise kernels.
+enum { LVSR_FLOW_OK = 0, LVSR_FLOW_TIMEOUT = 2, LVSR_FLOW_BAD_CLUSTER = 3 };
 static __constant__ unsigned g_flow_spin_limit = LVSR_SPIN_LIMIT;
+static __constant__ unsigned* g_flow_status = nullptr;
 __device__ __forceinline__ void st_flow_f32(float* p, float v) {
   asm volatile("st.relaxed.gpu.global.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+// Called every 1024 unsuccessful polls: true = stop waiting (this or another poller timed out).
+static __device__ __noinline__ bool flow_give_up(unsigned spins) {
+  unsigned* st = g_flow_status;
+  if (st == nullptr) {
+    if (spins > g_flow_spin_limit) __trap();
+    return false;
+  }
+  if (spins > g_flow_spin_limit) atomicCAS(st, 0u, (unsigned)LVSR_FLOW_TIMEOUT);
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(st) : "memory");
+  return v != 0u;
 }
 __device__ __forceinline__ float ld_flow_f32(const float* p) {
   unsigned v, spins = 0;
   while (true) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     if (v != LVSR_SENTINEL) break;
-    if (++spins > g_flow_spin_limit) __trap();     // a value that never arrives must fail the launch, not hang
+    if (((++spins) & 1023u) == 0u && flow_give_up(spins)) { v = 0u; break; }
   }
   return __uint_as_float(v);
 }
@@ -109,7 +146,7 @@ __device__ __forceinline__ float4 ld_flow_f4(const float* p) {
                  : "l"(p)
                  : "memory");
     if (x != LVSR_SENTINEL && y != LVSR_SENTINEL && z != LVSR_SENTINEL && w != LVSR_SENTINEL) break;
-    if (++spins > g_flow_spin_limit) __trap();
+    if (((++spins) & 1023u) == 0u && flow_give_up(spins)) { x = y = z = w = 0u; break; }
   }
   return make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(w));
 }

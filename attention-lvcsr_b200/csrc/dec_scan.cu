@@ -210,6 +210,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   const int cluster_id = bid / cs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = a.B, C = a.C, E = a.E, M = a.M;
+  // The whole plan (chunk capacity, shared-memory carve-up, who owns which row) assumes clusters of
+  // a.cs CTAs.  A launch path that loses the cluster attribute (seen under Nsight Compute when the
+  // launch also carried the cooperative attribute: the kernel ran with 1-CTA clusters, overran its
+  // shared-memory chunks and produced NaNs) must not compute anything: every CTA sees the same
+  // mismatch and leaves before the first barrier.
+  if (cs != a.cs) {
+    if (bid == 0 && tid == 0 && a.status) atomicCAS(a.status, 0u, (unsigned)LVSR_FLOW_BAD_CLUSTER);
+    return;
+  }
 
   // ---- who synchronises with whom --------------------------------------------------------
   // island mode: the batch is cut into islands of <= 16 rows; an island's CTAs (its rows'
@@ -285,6 +294,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       a.trace[((size_t)trace_slot * a.L + i) * 9 + (j)] = global_ns();                      \
   } while (0)
   for (int i = 0; i < a.L; ++i) {
+#ifdef LVSR_DEC_DEBUG
+    if (bid == 0 && tid == 0) g_dbg_step = i;     // approximate (CTA 0's step)
+#endif
     DS_STAMP(0);
     // No barriers or flags below: every cross-CTA value lives in a per-step, sentinel-filled
     // buffer and is polled by its consumers (common.cuh).  Phases of different rows / tiles
@@ -397,16 +409,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   cluster.sync();   // no CTA exits while a peer may still address its shared memory
 }
 
-int g_sms = 0;
-int sm_count() {
-  if (g_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms <= 0) g_sms = 148;
-  }
-  return g_sms;
-}
+int sm_count() { return device_sm_count(); }
 
 int round_up8(int x) { return (x + 7) & ~7; }
 bool kper_ok(int ktot) {
@@ -471,13 +474,14 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
     cfg.blockDim = dim3(DS_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    // Co-residency of the whole grid comes from the occupancy query below (one CTA per SM, grid <=
+    // max active clusters), NOT from the cooperative-launch attribute: combined with a cluster
+    // dimension that attribute made profilers drop the cluster shape (round-1 NaN under ncu).
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeCooperative;
-    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
@@ -495,20 +499,34 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       cfg.dynamicSmemBytes = smem;
     }
     if (R * cs > G) continue;        // not enough clusters for one per row: try a smaller cluster
-    cfg.numAttrs = 2;
     {
       // profilers slow the kernel down by orders of magnitude: let them raise the hang guard
       const char* sl = getenv("LVSR_FLOW_SPIN_LIMIT");
       const unsigned lim = sl ? (unsigned)strtoul(sl, nullptr, 10) : LVSR_SPIN_LIMIT;
       LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_spin_limit, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, stream));
+      LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_status, &a.status, sizeof(a.status), 0, cudaMemcpyHostToDevice, stream));
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      continue;                      // no non-cooperative fallback: a partial grid would deadlock
+      continue;
     }
     g_launch_count++;
     *supported = 1;
+#ifdef LVSR_DEC_DEBUG
+    {
+      LVSR_CUDA_OK(cudaStreamSynchronize(stream));
+      unsigned long long ev[64]; unsigned int cnt = 0;
+      LVSR_CUDA_OK(cudaMemcpyFromSymbol(&cnt, g_dbg_count, sizeof(cnt)));
+      LVSR_CUDA_OK(cudaMemcpyFromSymbol(ev, g_dbg_events, sizeof(ev)));
+      fprintf(stderr, "[dec debug] G=%d cs=%d NaN sightings: %u\n", G, cs, cnt);
+      for (unsigned k = 0; k < cnt && k < 64; ++k)
+        fprintf(stderr, "   stage %llu step~%llu cta %llu tid %llu idx %llu\n", ev[k] >> 56, (ev[k] >> 48) & 0xff,
+                (ev[k] >> 32) & 0xffff, (ev[k] >> 16) & 0xffff, ev[k] & 0xffff);
+      cnt = 0;
+      LVSR_CUDA_OK(cudaMemcpyToSymbol(g_dbg_count, &cnt, sizeof(cnt)));
+    }
+#endif
     return 0;
   }
   return 0;

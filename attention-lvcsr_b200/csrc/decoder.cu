@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(256) readout_kernel(ReadoutArgs a) {
   for (int q = 0; q < 4; ++q) {
     const int v = lane + q * 32;
     if (v < a.V) {
-      const float cost = -((logit[q] - vmax) - lse);
+      float cost = -((logit[q] - vmax) - lse);
+      if (a.poison && *a.poison != 0u) cost = __int_as_float(0x7fc00000);   // producer kernel reported a failed launch
       if (a.costs_all) a.costs_all[(long long)r * a.V + v] = cost;
       if (a.costs_picked && v == lab) a.costs_picked[r] = cost * (a.lmask ? a.lmask[r] : 1.f);
     }
@@ -192,6 +193,13 @@ __global__ void gather_time_kernel(float* dst, const float* src, int Tout, int k
     const long long t = i / row_elems, e = i % row_elems;
     dst[i] = src[t * k * row_elems + e];
   }
+}
+
+__global__ void count_sentinels_kernel(const unsigned* p, long long n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += p[i] == LVSR_SENTINEL ? 1u : 0u;
+  if (c) atomicAdd(out, c);
 }
 
 inline int grid_for(long long n) { return (int)std::min<long long>(2048, std::max<long long>(1, (n + 255) / 256)); }
@@ -245,6 +253,19 @@ int onehot_rows(float* dst, int R, int N, cudaStream_t stream) {
   if (total <= 0) return 0;
   onehot_rows_kernel<<<grid_for(total), 256, 0, stream>>>(dst, total, N);
   LVSR_LAUNCH_CHECK();
+  return 0;
+}
+int count_sentinels(const float* p, long long n, long long* host_count, cudaStream_t stream) {
+  unsigned long long* d = nullptr;
+  LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(*d)));
+  cudaMemsetAsync(d, 0, sizeof(*d), stream);
+  if (n > 0) count_sentinels_kernel<<<grid_for(n), 256, 0, stream>>>(reinterpret_cast<const unsigned*>(p), n, d);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return set_error("count_sentinels failed: %s", cudaGetErrorString(e));
+  *host_count = (long long)h;
   return 0;
 }
 int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream) {

@@ -311,10 +311,11 @@ int gemm_tc(const float* A, float* A_hi, float* A_lo, int M, int K, const float*
   if (int rc = make_map(&ma_lo, A_lo, M, K)) return rc;
   if (int rc = make_map(&mb_hi, Wt_hi, N, K)) return rc;
   if (int rc = make_map(&mb_lo, Wt_lo, N, K)) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[LVSR_MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
     LVSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    configured = true;
+    configured[dev] = true;
   }
   TcGemmParams p;
   p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc;

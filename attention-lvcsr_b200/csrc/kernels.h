@@ -119,6 +119,7 @@ struct ReadoutArgs {
   const float* lmask;      // [R] or nullptr (multiplies the picked cost)
   float* costs_all;        // [R, V] or nullptr
   float* costs_picked;     // [R] or nullptr
+  const unsigned* poison;  // optional launch-status word of the producer: non-zero -> every cost is NaN
 };
 int readout_costs(const ReadoutArgs& a, cudaStream_t stream);
 
@@ -146,6 +147,7 @@ struct DecScanArgs {
   float* hr_all;                       // [L, B, C] reset-gated states (the only gate value that crosses CTAs)
   float* rowpos_all;                   // [L+1, B]; rowpos_all[0] = 0
   unsigned long long* trace;           // optional debug stamps, or nullptr
+  unsigned* status;                    // launch status word (common.cuh: LVSR_FLOW_*), zeroed by the caller
   int Tp, B, L, M, E, C, K, n, normalizer;
   // derived by the planner
   int cs, tc_cap, nrg, nc1, nc2, nc3;
@@ -158,6 +160,7 @@ int fill_f32(float* p, long long n, float v, cudaStream_t stream);
 int fill_i64(long long* p, long long n, long long v, cudaStream_t stream);
 int broadcast_rows(float* dst, const float* src, int R, int N, cudaStream_t stream);   // dst[r,:] = src[:]
 int onehot_rows(float* dst, int R, int N, cudaStream_t stream);                         // dst[r,:] = e_0
+int count_sentinels(const float* p, long long n, long long* host_count, cudaStream_t stream);   // synchronises
 int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream);
 int gather_time_subsample(float* dst, const float* src, int Tout, int k, long long row_elems,
                           cudaStream_t stream);                                         // dst[t] = src[t*k]

@@ -285,6 +285,15 @@ class SpeechRecognizer(object):
             t = t.to(dtype)
         return t.contiguous()
 
+    def launch_status(self):
+        """(status, stepwise_fallbacks) of the persistent decoder (lvsr_model_status): status 0 = the last
+        cost_matrix launch completed; the counter says how often a failed launch was re-run step-wise."""
+        import ctypes as C
+        lib, h = _lib.load(), self._require_ready()
+        st, fb = C.c_int32(), C.c_int64()
+        _lib.check(lib.lvsr_model_status(h, C.byref(st), C.byref(fb)))
+        return int(st.value), int(fb.value)
+
     def encoded_length(self, T):
         return int(_lib.load().lvsr_encoded_length(self._require_ready(), int(T)))
 
@@ -298,9 +307,13 @@ class SpeechRecognizer(object):
         lib, h = _lib.load(), self._require_ready()
         x = self._dev(recordings, torch.float32)
         m = self._dev(recordings_mask, torch.float32)
+        if x.dim() != 3:
+            raise ValueError("encode: recordings [T,B,F] expected")
         T, B, F = x.shape
         if F != self.net["num_features"]:
             raise ValueError("expected %d features, got %d" % (self.net["num_features"], F))
+        if m is not None and tuple(m.shape) != (T, B):
+            raise ValueError("encode: recordings_mask must be [%d, %d], got %s" % (T, B, tuple(m.shape)))
         Tp = self.encoded_length(T)
         att = torch.empty((Tp, B, self.dim_encoded), dtype=torch.float32, device=self.device)
         attm = torch.empty((Tp, B), dtype=torch.float32, device=self.device)
@@ -332,8 +345,18 @@ class SpeechRecognizer(object):
         ym = self._dev(labels_mask, torch.float32)
         att = self._dev(attended, torch.float32)
         attm = self._dev(attended_mask, torch.float32)
+        if y.dim() != 2 or att.dim() != 3 or attm.dim() != 2:
+            raise ValueError("cost_matrix: labels [L,B], attended [T',B,E], attended_mask [T',B] expected")
         L, B = y.shape
         Tp = att.shape[0]
+        if L < 1 or B < 1 or Tp < 1:
+            raise ValueError("cost_matrix: empty labels or attended sequence")
+        if tuple(att.shape) != (Tp, B, self.dim_encoded):
+            raise ValueError("cost_matrix: attended must be [%d, %d, %d], got %s" % (Tp, B, self.dim_encoded, tuple(att.shape)))
+        if tuple(attm.shape) != (Tp, B):
+            raise ValueError("cost_matrix: attended_mask must be [%d, %d], got %s" % (Tp, B, tuple(attm.shape)))
+        if ym is not None and tuple(ym.shape) != (L, B):
+            raise ValueError("cost_matrix: labels_mask must be [%d, %d], got %s" % (L, B, tuple(ym.shape)))
         costs = torch.empty((L, B), dtype=torch.float32, device=self.device)
         extra = {}
         if return_all:
@@ -363,8 +386,20 @@ class SpeechRecognizer(object):
         y = np.ascontiguousarray(labels, dtype=np.int64)
         self._check_labels(y)
         ym = None if labels_mask is None else np.ascontiguousarray(labels_mask, dtype=np.float32)
-        T, B, _ = x.shape
+        if x.ndim != 3 or y.ndim != 2:
+            raise ValueError("cost: recordings [T,B,F] and labels [L,B] expected")
+        T, B, F = x.shape
         L = y.shape[0]
+        if F != self.net["num_features"]:
+            raise ValueError("expected %d features, got %d" % (self.net["num_features"], F))
+        if T < 1 or B < 1 or L < 1:
+            raise ValueError("cost: empty batch")
+        if m is not None and m.shape != (T, B):
+            raise ValueError("cost: recordings_mask must be [%d, %d], got %s" % (T, B, m.shape))
+        if y.shape != (L, B):
+            raise ValueError("cost: labels must be [L, %d], got %s" % (B, y.shape))
+        if ym is not None and ym.shape != (L, B):
+            raise ValueError("cost: labels_mask must be [%d, %d], got %s" % (L, B, ym.shape))
         costs = np.empty((L, B), dtype=np.float32)
         torch = self._torch()
         with torch.cuda.device(self.device):

@@ -78,6 +78,13 @@ int lvsr_model_set_param(lvsr_model* m, const char* name, const float* values_ho
 int lvsr_model_get_param(const lvsr_model* m, const char* name, float* values_host, int64_t count);
 /* Re-derive the packed kernel-side weights after parameters changed. */
 int lvsr_model_finalize(lvsr_model* m);
+/* Launch status of the persistent teacher-forced decoder of the LAST lvsr_cost_matrix call on this
+ * handle (synchronises with the device): 0 = ok, 2 = a hand-over value never arrived within the
+ * polling limit, 3 = the launch lost its cluster shape.  On a non-zero status the costs of that call
+ * are NaN (never plausible garbage); lvsr_recognizer_cost_host re-runs such a call on the step-wise
+ * kernels by itself and counts it in *stepwise_fallbacks (may be NULL).  No reference counterpart:
+ * Theano raises from inside the compiled function instead. */
+int lvsr_model_status(lvsr_model* m, int32_t* launch_status, int64_t* stepwise_fallbacks);
 
 /* ---- encoder: BeamSearch.context_computer / Encoder.apply -------------------------
  * (libs/blocks/blocks/search.py:97-99; lvsr/bricks/__init__.py:71-78).

@@ -134,3 +134,57 @@ def test_shape_errors_are_reported_not_crashed():
     with pytest.raises((RuntimeError, ValueError)):
         rec.cost_matrix(bad, lm, att, attm)
     assert pkg is not None
+
+
+def test_mismatched_argument_shapes_raise_value_error():
+    """Every array handed to the C ABI is shape-checked on the host first (a mismatch
+    used to read out of bounds)."""
+    _torch()
+    cfg = O.make_config(**SMALL)
+    rec = make_recognizer(cfg, O.init_params(cfg, seed=1, scale=10.0))
+    x, m, labels, lm = O.synthetic_batch(cfg, B=3, T=16, seed=1)
+    att, attm = rec.encode(x, m)
+    with pytest.raises(ValueError):
+        rec.cost(x[:, :, :-1], m, labels, lm)            # feature width
+    with pytest.raises(ValueError):
+        rec.cost(x, m[:-1], labels, lm)                  # recordings_mask length
+    with pytest.raises(ValueError):
+        rec.cost(x, m, labels[:, :-1], lm)               # labels batch
+    with pytest.raises(ValueError):
+        rec.cost(x, m, labels, lm[:-1])                  # labels_mask length
+    with pytest.raises(ValueError):
+        rec.encode(x, m[:, :-1])
+    with pytest.raises(ValueError):
+        rec.cost_matrix(labels, lm, att[:, :-1], attm)   # attended batch != labels batch
+    with pytest.raises(ValueError):
+        rec.cost_matrix(labels, lm, att[:, :, :-1], attm)
+    with pytest.raises(ValueError):
+        rec.cost_matrix(labels, lm, att, attm[:-1])
+    with pytest.raises(ValueError):
+        rec.cost_matrix(labels, lm[:, :-1], att, attm)
+    got = rec.cost(x, m, labels, lm)                     # the handle still works afterwards
+    assert np.isfinite(got).all()
+
+
+def test_model_on_second_device_while_first_is_current():
+    """A handle lives on the device that was current at creation; later calls run there whatever
+    device the caller has current (per-device function attributes, DeviceGuard in api.cu)."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = O.make_config(**SMALL)
+    params = O.init_params(cfg, seed=1, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=3, T=16, seed=1)
+    want = O.recognizer_cost(cfg, params, x, m, labels, lm)
+    pkg = package()
+    for dev in ("cuda:1", "cuda:0"):
+        rec = pkg.SpeechRecognizer(
+            input_dims={"recordings": 40}, input_num_chars={}, eos_label=cfg["eos_label"], num_phonemes=32,
+            dim_dec=128, dims_bidir=[128], subsample=[1], conv_n=8, conv_num_filters=10,
+            post_merge_dims=[128], post_merge_activation=pkg.Maxout(2), device=torch.device(dev))
+        rec.set_parameter_values(params)
+        torch.cuda.set_device(0)
+        assert rel_err(rec.cost(x, m, labels, lm), want) < 1e-4
+        att, attm = rec.encode(x, m)
+        assert str(att.device) == dev
+        assert rel_err(rec.cost_matrix(labels, lm, att, attm).cpu().numpy(), want) < 1e-4
