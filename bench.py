@@ -138,6 +138,13 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+# DRAM traffic of ONE dec_scan_kernel launch at the metric configuration (dram__bytes_read.sum +
+# dram__bytes_write.sum of the `ncu --set full` capture summarised in profiles/r2a_summary.md /
+# profiles/r2a_dec_scan_metrics.csv), and the L2->SM bytes of the same capture.
+NCU_DEC_SCAN = {"config": (64, 1000, 125), "dram_bytes": 2.672282e9 + 1.510394e9, "l2_to_sm_bytes": 13.303018e9,
+                "l2_hit_pct": 70.18, "source": "profiles/r2a_dec_scan_metrics.csv"}
+
+
 def attention_step_bytes(B, Tw, M, E):
     """ALGORITHMIC bytes of one attention+decoder step: read P_cut and H_cut
     once, read alpha_prev + mask, write alpha + energies."""
@@ -345,7 +352,16 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": kern,
                      "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": (NCU_DEC_SCAN["dram_bytes"] if (prof["dec_scan"]["launches"] > 0 and
+                                 (W["B"], W["T"], W["L"]) == NCU_DEC_SCAN["config"]) else None),
+                     "traffic_source": NCU_DEC_SCAN["source"],
+                     "l2_to_sm_GBps": (NCU_DEC_SCAN["l2_to_sm_bytes"] / (k_us * 1e-6) / 1e9
+                                       if (prof["dec_scan"]["launches"] > 0 and k_us > 0 and
+                                           (W["B"], W["T"], W["L"]) == NCU_DEC_SCAN["config"]) else None),
+                     "binds": "latency (dependent phases at 25 % occupancy); P and H are L2-resident (hit rate 70 %), "
+                              "HBM moves about half the algorithmic bytes",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": launch_bytes, "us_per_launch": k_us,
                      "decoder_step_us": dec_us,
                      "decoder_step_frac": (step_bytes / (dec_us * 1e-6) / 1e9 / peaks["hbm_gbs"]) if dec_us > 0 else 0.0,
