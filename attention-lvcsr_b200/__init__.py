@@ -10,8 +10,12 @@ include/lvsr_b200.h) and the host-side mirror of the reference's operator surfac
 from . import _lib  # noqa: F401
 from .bricks import (Constant, GatedRecurrent, Identity, IsotropicGaussian, Maxout,  # noqa: F401
                      Orthogonal, Rectifier, Tanh, Uniform)
+from . import algorithms  # noqa: F401
+from .algorithms import (AdaDelta, BurnIn, CompositeRule, GradientDescent, Momentum, RemoveNotFinite,  # noqa: F401
+                         Restrict, Scale, StepClipping, VariableClipping, step_rule_from_config)
 from .recognizer import SpeechRecognizer  # noqa: F401
 from .search import BeamSearch, CandidateNotFoundError  # noqa: F401
 
-__all__ = ["SpeechRecognizer", "BeamSearch", "CandidateNotFoundError", "Maxout", "Rectifier", "Tanh",
+__all__ = ["GradientDescent", "CompositeRule", "StepClipping", "Momentum", "AdaDelta", "VariableClipping", "Restrict",
+           "RemoveNotFinite", "BurnIn", "Scale", "step_rule_from_config", "SpeechRecognizer", "BeamSearch", "CandidateNotFoundError", "Maxout", "Rectifier", "Tanh",
            "Identity", "GatedRecurrent", "IsotropicGaussian", "Constant", "Orthogonal", "Uniform"]

@@ -43,6 +43,13 @@ class LvsrConfig(C.Structure):
     ]
 
 
+class LvsrTrainConfig(C.Structure):
+    """Mirror of ``lvsr_train_config`` (include/lvsr_b200.h)."""
+    _fields_ = [("gradient_threshold", C.c_float), ("use_momentum", C.c_int32), ("scale", C.c_float),
+                ("momentum", C.c_float), ("use_adadelta", C.c_int32), ("decay_rate", C.c_float),
+                ("epsilon", C.c_float), ("max_norm", C.c_float), ("burn_in_steps", C.c_int32), ("decay", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/lvsr_b200.h declares
 _P = C.c_void_p
 _I = C.c_int32
@@ -56,6 +63,9 @@ SIGNATURES = {
     "lvsr_model_param_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "lvsr_model_set_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "lvsr_model_get_param": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    "lvsr_model_flat_size": (C.c_int64, [_P]),
+    "lvsr_model_param_offset": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lvsr_model_flat_params": (C.c_void_p, [_P]),
     "lvsr_model_finalize": (C.c_int, [_P]),
     "lvsr_model_status": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "lvsr_encoded_length": (C.c_int, [_P, _I]),
@@ -67,6 +77,10 @@ SIGNATURES = {
     "lvsr_logprobs": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "lvsr_next_states": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lvsr_recognizer_cost_host": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "lvsr_train_cost_and_grads": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P, _P, _P]),
+    "lvsr_train_apply_updates": (C.c_int, [_P, _P, C.c_float, C.POINTER(LvsrTrainConfig), _P]),
+    "lvsr_train_gradient_norm": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "lvsr_train_reset": (C.c_int, [_P]),
     "lvsr_launch_count": (C.c_int64, [C.c_int]),
     "lvsr_profile_enable": (C.c_int, [C.c_int]),
     "lvsr_profile_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.h"
+#include "model.h"
 
 namespace lvsr {
 
@@ -48,115 +48,11 @@ ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
 }
 
-// Stack-style device workspace.  Top-level API calls bump-allocate from one block; when
-// the block is too small the overflow is served by separate cudaMallocs and the block is
-// regrown at the end of the call, so a steady-state workload never allocates.
-struct Arena {
-  char* base = nullptr;
-  size_t cap = 0, off = 0, overflow_bytes = 0;
-  int depth = 0;
-  std::vector<void*> overflow;
-
-  void* alloc(size_t bytes) {
-    bytes = (bytes + 255) & ~(size_t)255;
-    if (off + bytes <= cap) {
-      void* p = base + off;
-      off += bytes;
-      return p;
-    }
-    void* p = nullptr;
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-    overflow.push_back(p);
-    overflow_bytes += bytes;
-    return p;
-  }
-  float* f32(size_t n) { return static_cast<float*>(alloc(n * sizeof(float))); }
-  long long* i64(size_t n) { return static_cast<long long*>(alloc(n * sizeof(long long))); }
-  int* i32(size_t n) { return static_cast<int*>(alloc(n * sizeof(int))); }
-
-  // Grow the block up front (only legal while nothing is allocated from it).
-  void reserve(size_t bytes, cudaStream_t stream) {
-    if (off != 0 || bytes <= cap) return;
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return;
-    if (base) cudaFree(base);
-    base = nullptr;
-    cap = 0;
-    if (cudaMalloc(reinterpret_cast<void**>(&base), bytes) == cudaSuccess) cap = bytes;
-    else cudaGetLastError();
-  }
-  void enter() { depth++; }
-  // returns non-zero on CUDA failure
-  int leave(cudaStream_t stream) {
-    depth--;
-    if (depth > 0) return 0;
-    const size_t used = off;
-    off = 0;
-    if (!overflow.empty()) {
-      if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
-      for (void* p : overflow) cudaFree(p);
-      overflow.clear();
-      if (base) cudaFree(base);
-      base = nullptr;
-      const size_t want = (size_t)((used + overflow_bytes) * 1.25) + (1 << 20);
-      overflow_bytes = 0;
-      cap = 0;
-      if (cudaMalloc(reinterpret_cast<void**>(&base), want) == cudaSuccess) cap = want;
-      else cudaGetLastError();
-    }
-    return 0;
-  }
-  void destroy() {
-    for (void* p : overflow) cudaFree(p);
-    overflow.clear();
-    if (base) cudaFree(base);
-    base = nullptr;
-    cap = off = 0;
-  }
-};
-
-struct Param {
-  std::string name;
-  int64_t shape[2];
-  int ndim;
-  int64_t count;
-  float* dev;
-};
-
 }  // namespace lvsr
 
 using namespace lvsr;
 
-struct lvsr_model {
-  lvsr_config cfg;
-  int device = 0;                   // the GPU this handle lives on (current device at lvsr_model_create)
-  int E;
-  std::vector<Param> params;
-  std::map<std::string, int> index;
-  // packed, kernel-side weights (rebuilt by finalize)
-  std::vector<float*> Wcat, bcat;   // per encoder layer: [Din, 6D], [6D]
-  float* Wd_cat = nullptr;          // [E, 3C] = [distribute gate_inputs (2C) | distribute inputs (C)]
-  float* Wb1 = nullptr;             // [E+C, 3C] = Wd_cat stacked on [state_to_gates | 0] (persistent decoder)
-  float* Wff_cat = nullptr;         // [Cfb, 3C] = [fork gate_inputs | fork inputs]
-  float* bff_cat = nullptr;         // [3C]
-  float* FF = nullptr;              // [(V+1), 3C] = lookup . Wff_cat + bff_cat
-  // K-major tf32 hi/lo splits of the dense-projection weights (tcgen05 path); null = SIMT path
-  std::vector<float*> Wcat_hi, Wcat_lo;
-  float *Wp_hi = nullptr, *Wp_lo = nullptr;
-  bool use_tc = true;
-  float v_bias = 0.f;               // host copy of energy_comp/linear.b
-  unsigned* status = nullptr;       // device word: launch status of the data-flow decoder (common.cuh LVSR_FLOW_*)
-  bool force_stepwise = false;      // set while a failed persistent launch is re-run on the step-wise kernels
-  long long dec_fallbacks = 0;      // how often that happened
-  bool finalized = false;
-  Arena ws;
-
-  float* P(const std::string& n) const {
-    auto it = index.find(n);
-    return it == index.end() ? nullptr : params[it->second].dev;
-  }
-};
-
-namespace {
+namespace lvsr {
 
 void add_param(lvsr_model* m, const std::string& name, int64_t d0, int64_t d1 = -1) {
   Param p;
@@ -170,15 +66,6 @@ void add_param(lvsr_model* m, const std::string& name, int64_t d0, int64_t d1 = 
   m->params.push_back(p);
 }
 
-const char* GEN = "/recognizer/generator";
-const char* TR = "/recognizer/generator/att_trans";
-const char* ATT = "/recognizer/generator/att_trans/conv_att";
-
-std::string enc_base(int l, int dir) {
-  char buf[128];
-  snprintf(buf, sizeof(buf), "/recognizer/encoder/bidir%d/%s", l, dir ? "backward" : "forward");
-  return buf;
-}
 
 // Blocks initialisation order (oracle/lvsr_oracle.py: param_shapes)
 void build_param_table(lvsr_model* m) {
@@ -231,23 +118,7 @@ int copy_cols(float* dst, int ld_dst, int col0, const float* src, int rows, int 
   return 0;
 }
 
-int check_ready(lvsr_model* m) {
-  LVSR_CHECK(m != nullptr, "null model");
-  if (!m->finalized) return lvsr_model_finalize(m);
-  return 0;
-}
 
-PriorParams prior_of(const lvsr_config& c) {
-  PriorParams p;
-  p.type = c.prior_type;
-  p.initial_begin = c.prior_initial_begin;
-  p.initial_end = c.prior_initial_end;
-  p.min_speed = c.prior_min_speed;
-  p.max_speed = c.prior_max_speed;
-  p.before = c.prior_before;
-  p.after = c.prior_after;
-  return p;
-}
 
 // take_glimpses for R rows: q = s.W_state, window, attention step.
 int glimpses(lvsr_model* m, const float* H, const float* P, const float* maskH, int Tp, int U,
@@ -346,29 +217,9 @@ size_t cost_ws_bytes(const lvsr_model* m, int Tp, int B, int L) {
   return f * sizeof(float) + (1 << 16);
 }
 
-// Every entry point runs on the handle's own GPU, whatever device the calling thread has current
-// (a handle is bound to the device that was current at lvsr_model_create).
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(const lvsr_model* m) {
-    if (!m) return;
-    int cur = 0;
-    if (cudaGetDevice(&cur) == cudaSuccess && cur != m->device) {
-      prev = cur;
-      cudaSetDevice(m->device);
-    }
-  }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
-struct ArenaScope {
-  lvsr_model* m;
-  cudaStream_t st;
-  ArenaScope(lvsr_model* mm, cudaStream_t s) : m(mm), st(s) { m->ws.enter(); }
-  ~ArenaScope() { m->ws.leave(st); }
-};
 
-}  // namespace
+}  // namespace lvsr
 
 extern "C" {
 
@@ -434,15 +285,21 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
   LVSR_CUDA_OK(cudaGetDevice(&m->device));
   m->E = 2 * cfg->dims_bidir[cfg->num_layers - 1];
   build_param_table(m);
+  int64_t total = 0;
   for (auto& p : m->params) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p.dev), (size_t)p.count * sizeof(float));
-    if (e != cudaSuccess) {
-      const std::string name = p.name;       // `p` dies with the model
-      lvsr_model_destroy(m);
-      return set_error("cudaMalloc(%s) failed: %s", name.c_str(), cudaGetErrorString(e));
-    }
-    cudaMemset(p.dev, 0, (size_t)p.count * sizeof(float));
+    p.offset = total;
+    total += (p.count + 63) & ~(int64_t)63;
   }
+  m->flat_count = total;
+  {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->flat), (size_t)total * sizeof(float));
+    if (e != cudaSuccess) {
+      lvsr_model_destroy(m);
+      return set_error("cudaMalloc(parameters, %lld floats) failed: %s", (long long)total, cudaGetErrorString(e));
+    }
+    cudaMemset(m->flat, 0, (size_t)total * sizeof(float));
+  }
+  for (auto& p : m->params) p.dev = m->flat + p.offset;
   if (cudaMalloc(reinterpret_cast<void**>(&m->status), 64) != cudaSuccess) {
     lvsr_model_destroy(m);
     return set_error("cudaMalloc(status) failed");
@@ -456,7 +313,7 @@ int lvsr_model_destroy(lvsr_model* m) {
   if (!m) return 0;
   DeviceGuard device_guard(m);
   cudaDeviceSynchronize();
-  for (auto& p : m->params) if (p.dev) cudaFree(p.dev);
+  if (m->flat) cudaFree(m->flat);
   for (float* p : m->Wcat) if (p) cudaFree(p);
   for (float* p : m->bcat) if (p) cudaFree(p);
   for (float* p : m->Wcat_hi) if (p) cudaFree(p);
@@ -469,6 +326,12 @@ int lvsr_model_destroy(lvsr_model* m) {
   if (m->bff_cat) cudaFree(m->bff_cat);
   if (m->FF) cudaFree(m->FF);
   if (m->status) cudaFree(m->status);
+  if (m->opt_velocity) cudaFree(m->opt_velocity);
+  if (m->opt_ms_step) cudaFree(m->opt_ms_step);
+  if (m->opt_ms_dx) cudaFree(m->opt_ms_dx);
+  if (m->opt_scratch) cudaFree(m->opt_scratch);
+  if (m->opt_desc) cudaFree(m->opt_desc);
+  m->tws.destroy();
   m->ws.destroy();
   delete m;
   return 0;
@@ -496,6 +359,14 @@ int lvsr_model_param_shape(const lvsr_model* m, int i, int64_t shape[2], int32_t
   *ndim = m->params[i].ndim;
   return 0;
 }
+int64_t lvsr_model_flat_size(const lvsr_model* m) { return m ? m->flat_count : 0; }
+int lvsr_model_param_offset(const lvsr_model* m, int i, int64_t* offset, int64_t* count) {
+  LVSR_CHECK(m && offset && i >= 0 && i < (int)m->params.size(), "bad parameter index %d", i);
+  *offset = m->params[i].offset;
+  if (count) *count = m->params[i].count;
+  return 0;
+}
+float* lvsr_model_flat_params(lvsr_model* m) { return m ? m->flat : nullptr; }
 int lvsr_model_set_param(lvsr_model* m, const char* name, const float* host, int64_t count) {
   DeviceGuard device_guard(m);
   LVSR_CHECK(m && name && host, "null argument");
@@ -521,8 +392,14 @@ int lvsr_model_get_param(const lvsr_model* m, const char* name, float* host, int
 int lvsr_model_finalize(lvsr_model* m) {
   DeviceGuard device_guard(m);
   LVSR_CHECK(m, "null model");
+  return finalize_on_stream(m, 0, true);
+}
+
+}  // extern "C"
+
+namespace lvsr {
+int finalize_on_stream(lvsr_model* m, cudaStream_t st, bool synchronise) {
   const lvsr_config& c = m->cfg;
-  cudaStream_t st = 0;
   if (m->Wcat.empty()) {
     int din = c.num_features;
     for (int l = 0; l < c.num_layers; ++l) {
@@ -606,10 +483,13 @@ int lvsr_model_finalize(lvsr_model* m) {
   if (c.energy_normalizer != LVSR_NORM_SOFTMAX)
     LVSR_CUDA_OK(cudaMemcpy(&m->v_bias, m->P(std::string(ATT) + "/energy_comp/linear.b"), sizeof(float),
                             cudaMemcpyDeviceToHost));
-  LVSR_CUDA_OK(cudaStreamSynchronize(st));
+  if (synchronise) LVSR_CUDA_OK(cudaStreamSynchronize(st));
   m->finalized = true;
   return 0;
 }
+}  // namespace lvsr
+
+extern "C" {
 
 int lvsr_encoded_length(const lvsr_model* m, int32_t T) {
   if (!m) return 0;

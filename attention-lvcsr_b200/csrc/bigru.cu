@@ -199,6 +199,14 @@ bigru_kernel(BiGruArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   float h_own = h0[u_warp + unit2];                                        // h(row2, unit2), same for every row at t = -1
+  // training tape: broadcast initial state into its boundary slot of hext
+  if (a.hext != nullptr) {
+    for (int i = tid; i < RB * UC; i += NWARP * 32) {
+      const int r = i / UC, u = rank * UC + i % UC;
+      if (row0 + r < a.B)
+        a.hext[((long long)(dir ? a.T + 1 : 0) * a.B + row0 + r) * (2 * D) + dir * D + u] = h0[u];
+    }
+  }
 
   const int T = a.T, B = a.B;
   const long long pre_ld = 6LL * D;                       // [A | Gz | Gr] per direction
@@ -210,6 +218,9 @@ bigru_kernel(BiGruArgs a) {
   const float* pg_ptr = pre_dir + ((long long)t * B + row0 + row1) * pre_ld + (is_z ? D : 2 * D) + u_warp + unit1;
   const float* pa_ptr = pre_dir + ((long long)t * B + row0 + row2) * pre_ld + u_warp + unit2;
   const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + row2 : nullptr;
+  // tape slots of this lane's gate / candidate (same addresses the pre-activations are read from)
+  float* tg_ptr = a.tape ? a.tape + (pg_ptr - a.pre) : nullptr;
+  float* ta_ptr = a.tape ? a.tape + (pa_ptr - a.pre) : nullptr;
   const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
   float pg = 0.f, pa = 0.f, pm = 1.f;
   auto prefetch = [&]() {
@@ -280,6 +291,10 @@ bigru_kernel(BiGruArgs a) {
     BG_STAMP(1);
     warp_reduce_scatter<N1, CG>(acc1, lane);
     const float gate = fast_sigmoid(acc1[0] + g_cur);                    // z or r of (row1, unit1)
+    if (tg_ptr != nullptr) {
+      if (ok1) *tg_ptr = gate;
+      tg_ptr += pre_step;
+    }
     const float hr_mine = __shfl_sync(0xffffffffu, h_own, src_hold) * gate;   // meaningful on reset-gate lanes
     {
       const float x = __shfl_sync(0xffffffffu, hr_mine, src_hr[0]), y = __shfl_sync(0xffffffffu, hr_mine, src_hr[1]);
@@ -321,6 +336,10 @@ bigru_kernel(BiGruArgs a) {
     {
       const float zg = __shfl_sync(0xffffffffu, gate, src_z);            // update gate of (row2, unit2)
       const float cand = fast_tanh(acc2[0] + a_cur);
+      if (ta_ptr != nullptr) {
+        if (ok2 && (kg & 1) == 0) *ta_ptr = cand;       // the lane pair kg, kg ^ 1 holds the same value
+        ta_ptr += pre_step;
+      }
       float hn = cand * zg + h_own * (1.f - zg);
       hn = m_cur * hn + (1.f - m_cur) * h_own;
       h_own = hn;
@@ -329,6 +348,9 @@ bigru_kernel(BiGruArgs a) {
       if (sender) st_async_v4(dst_h, x, y, z, w, rbar_h);
       if (sub_phase == 0 && peer == 0 && row0 + rowg < B)
         *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
+            make_float4(x, y, z, w);
+      if (a.hext != nullptr && peer == 0 && row0 + rowg < B)
+        *reinterpret_cast<float4*>(a.hext + ((long long)(t + 1) * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
             make_float4(x, y, z, w);
     }
     BG_STAMP(5);

@@ -5,8 +5,12 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include -I."
 OBJS=()
-for f in gemm gemm_tc bigru attention decoder dec_scan api; do
-  if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ kernels.h -nt "$f.o" ] || [ common.cuh -nt "$f.o" ] || [ attention_row.cuh -nt "$f.o" ] || [ ../../include/lvsr_b200.h -nt "$f.o" ]; then
+for f in gemm gemm_tc bigru bigru_bwd attention decoder dec_scan train api; do
+  stale=0
+  for h in kernels.h common.cuh attention_row.cuh model.h ../../include/lvsr_b200.h; do
+    if [ "$h" -nt "$f.o" ]; then stale=1; fi
+  done
+  if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ $stale = 1 ]; then
     echo "nvcc $f.cu"
     $NVCC $FLAGS "$@" -c "$f.cu" -o "$f.o"
   fi

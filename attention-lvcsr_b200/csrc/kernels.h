@@ -43,9 +43,27 @@ struct BiGruArgs {
   const float *Wg_b, *Ws_b, *h0_b;   // backward
   float* out;              // [ceil(T/subsample), B, 2D] (forward units first)
   int T, B, D, subsample;
+  // training only (both null for inference): the tape the backward scan reads
+  float* tape;             // = pre, written in place: candidate c over the inputs slot, z / r over the gate slots
+  float* hext;             // [(T+2), B, 2D]: slot t+1 = states after time t; slot 0 (forward half) and slot T+1
+                           // (backward half) = the broadcast initial states
 };
 bool bigru_supported(int D);
 int bigru_layer(const BiGruArgs& a, cudaStream_t stream);
+
+// ---- bigru_bwd.cu: reverse-time scan of one layer (training) ------------------------------
+struct BiGruBwdArgs {
+  float* tape;             // [T*B, 6D] in: c | z | r per direction (forward's tape); out: dA | dGz | dGr
+  const float* hext;       // [(T+2), B, 2D] (see BiGruArgs)
+  const float* mask;       // [T, B] view or nullptr
+  long long mask_tstride;
+  const float* dout;       // [ceil(T/subsample), B, 2D] gradient of the layer's (subsampled) output
+  const float *Wg_f, *Ws_f, *Wg_b, *Ws_b;
+  float* hr_out;           // [T, B, 2D]: h_prev * r (operand of the state_to_state gradient)
+  float* dh0;              // [2, B, D]: gradient of the broadcast initial state, per direction and row
+  int T, B, D, subsample;
+};
+int bigru_layer_backward(const BiGruBwdArgs& a, cudaStream_t stream);
 
 // ---- attention.cu -------------------------------------------------------------------
 struct PriorParams {

@@ -76,6 +76,12 @@ int lvsr_model_param_shape(const lvsr_model* m, int index, int64_t shape[2], int
 /* Model.set_parameter_values / get_parameter_values (lvsr/bricks/recognizer.py:408-412). */
 int lvsr_model_set_param(lvsr_model* m, const char* name, const float* values_host, int64_t count);
 int lvsr_model_get_param(const lvsr_model* m, const char* name, float* values_host, int64_t count);
+/* All parameters live in ONE device allocation ("flat" layout: parameter i at float offset
+ * lvsr_model_param_offset, 256-byte aligned, padding zero).  Gradients, optimizer state and the
+ * gradient all-reduce of the training step use buffers of the same layout and size. */
+int64_t lvsr_model_flat_size(const lvsr_model* m);
+int lvsr_model_param_offset(const lvsr_model* m, int index, int64_t* offset, int64_t* count);
+float* lvsr_model_flat_params(lvsr_model* m);     /* device pointer; call lvsr_model_finalize after writing through it */
 /* Re-derive the packed kernel-side weights after parameters changed. */
 int lvsr_model_finalize(lvsr_model* m);
 /* Launch status of the persistent teacher-forced decoder of the LAST lvsr_cost_matrix call on this
@@ -135,6 +141,38 @@ int lvsr_next_states(lvsr_model* m, const float* attended_dev, const float* prep
 int lvsr_recognizer_cost_host(lvsr_model* m, const float* recordings_host, const float* mask_host,
                               const int64_t* labels_host, const float* labels_mask_host,
                               int32_t T, int32_t B, int32_t L, float* costs_host, void* stream);
+
+/* ---- training step: GradientDescent._function -------------------------------------------------
+ * (libs/blocks/blocks/algorithms/__init__.py:244-256,284-287 as assembled by lvsr/main.py:340-345,480-519).
+ * Split in two so a data-parallel caller can all-reduce the gradient buffer in between:
+ *
+ *   lvsr_train_cost_and_grads: forward + backward of one batch (device pointers, layouts as lvsr_encoder_forward /
+ *     lvsr_cost_matrix).  cost_dev[0] = gscale * sum(cost_matrix); grads_dev (lvsr_model_flat_size floats, flat
+ *     parameter layout) = gscale * d sum(cost_matrix) / d parameter.  Single GPU: gscale = 1/B gives the reference's
+ *     cost = sum / batch_size.  N GPUs: pass gscale = 1, all-reduce(sum) grads_dev, then apply with
+ *     gscale = 1 / global batch.  Softmax energy normaliser only.
+ *   lvsr_train_apply_updates: grads_dev *= gscale (+ 2 decay W on WEIGHT parameters), then the CompositeRule of
+ *     lvsr/main.py:509-516: StepClipping(gradient_threshold) -> Momentum(scale, momentum) -> AdaDelta(decay_rate,
+ *     epsilon) -> Restrict(VariableClipping(max_norm, axis=0), WEIGHT parameters) -> RemoveNotFinite(0.0) -> BurnIn,
+ *     parameter -= step, and the kernel-side weights are re-packed.  grads_dev holds the steps afterwards.
+ *     Optimizer state lives in the handle (lvsr_train_reset clears it). */
+typedef struct {
+  float gradient_threshold;        /* StepClipping threshold, 0 = off (B/algorithms/__init__.py:610-643)        */
+  int32_t use_momentum;            /* 'momentum' in config['training']['rules'] (lvsr/main.py:483-486)          */
+  float scale, momentum;           /* Momentum(learning_rate=scale, momentum)                                   */
+  int32_t use_adadelta;            /* 'adadelta' in rules                                                        */
+  float decay_rate, epsilon;       /* AdaDelta(decay_rate, epsilon), :464-516                                    */
+  float max_norm;                  /* regularization.max_norm, 0 = off (lvsr/main.py:490-505)                    */
+  int32_t burn_in_steps;           /* BurnIn(num_steps), lvsr/algorithms.py:19-43                                */
+  float decay;                     /* regularization.decay: + decay * ||WEIGHT parameters||^2 (lvsr/main.py:419-421) */
+} lvsr_train_config;
+int lvsr_train_cost_and_grads(lvsr_model* m, const float* recordings_dev, const float* mask_dev,
+                              const int64_t* labels_dev, const float* labels_mask_dev, int32_t T, int32_t B,
+                              int32_t L, float gscale, float* cost_dev, float* grads_dev, void* stream);
+int lvsr_train_apply_updates(lvsr_model* m, float* grads_dev, float gscale, const lvsr_train_config* tc,
+                             void* stream);
+int lvsr_train_gradient_norm(lvsr_model* m, float* norm_host);   /* total_gradient_norm of the last update (synchronises) */
+int lvsr_train_reset(lvsr_model* m);
 
 /* Counters for bench.py: number of kernels this library launched since the last reset. */
 int64_t lvsr_launch_count(int reset);

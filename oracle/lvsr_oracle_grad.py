@@ -196,7 +196,7 @@ def cost_and_grads(cfg, params, recordings, recordings_mask, labels, labels_mask
         out[k] = np.zeros(v.shape) if g is None else g.numpy().copy()
     if return_costs:
         return float(cost.detach()), out, costs.detach().numpy()
-    return float(cost), out
+    return float(cost.detach()), out
 
 
 # --------------------------------------------------------------------------

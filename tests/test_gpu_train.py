@@ -1,0 +1,149 @@
+"""Training step on the GPU against the gradient / optimizer oracle (oracle/lvsr_oracle_grad.py):
+gradients of every parameter (1e-4 of the parameter's largest gradient entry + a small absolute floor),
+the cost, and parameters after updates with the step-rule chain of lvsr/main.py:480-519."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from helpers import O, PYRAMID, WSJ, make_recognizer, package
+from oracle import lvsr_oracle_grad as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _grad_errors(got, want):
+    errs = {}
+    for k, w in want.items():
+        scale = max(np.abs(w).max(), 1e-30)
+        errs[k] = float(np.abs(got[k].astype(np.float64) - w).max() / scale)
+    return errs
+
+
+def _check_grads(cfg, params, batch, tol=1e-4, atol_frac=1e-6):
+    pkg = package()
+    rec = make_recognizer(cfg, params)
+    algo = pkg.GradientDescent(recognizer=rec, step_rule=pkg.CompositeRule([pkg.RemoveNotFinite(0.0)]))
+    cost, grads = algo.cost_and_gradients(dict(zip(algo.SOURCES, batch)))
+    want_cost, want = G.cost_and_grads(cfg, params, *batch)
+    assert abs(cost - want_cost) <= 1e-4 * abs(want_cost), (cost, want_cost)
+    gmax = max(np.abs(w).max() for w in want.values())
+    errs = _grad_errors(grads, want)
+    bad = {}
+    for k, e in errs.items():
+        # relative to the parameter's own largest gradient entry, with a floor relative to the model's largest
+        floor = atol_frac * gmax / max(np.abs(want[k]).max(), 1e-30)
+        if e > tol + floor:
+            bad[k] = (e, float(np.abs(want[k]).max()))
+    worst = max(errs.values())
+    print("cost", cost, "worst rel grad err %.2e" % worst, "of", len(errs), "parameters")
+    assert not bad, bad
+    return algo, rec
+
+
+PRIORS = [None, dict(type="window_around_median", before=5, after=7),
+          dict(type="expanding", initial_begin=0, initial_end=6, min_speed=0.7, max_speed=2.2)]
+
+
+@pytest.mark.parametrize("prior", PRIORS, ids=lambda p: "default" if p is None else p["type"])
+def test_gradients_match_oracle_pyramid(prior):
+    _torch()
+    cfg = O.make_config(prior=prior, **PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    batch = O.synthetic_batch(cfg, B=6, T=56, seed=21)
+    _check_grads(cfg, params, batch)
+
+
+def test_gradients_match_oracle_wsj_architecture():
+    """4-layer pyramidal BiGRU(256) (8-CTA clusters in the BPTT kernel), M=512, n=100, 2 label-masked rows."""
+    _torch()
+    cfg = O.make_config(**WSJ)
+    params = O.init_params(cfg, seed=1, scale=10.0)
+    batch = O.synthetic_batch(cfg, B=5, T=48, seed=3)
+    _check_grads(cfg, params, batch)
+
+
+def test_gradients_island_batch_no_masks():
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=7, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=18, T=40, seed=12)
+    _check_grads(cfg, params, (x, None, labels, None))
+
+
+@pytest.mark.parametrize("rules,max_norm", [(("momentum", "adadelta"), 1.0), (("momentum",), 0.0), (("adadelta",), 0.5)])
+def test_training_steps_match_oracle(rules, max_norm):
+    """Two process_batch calls == two oracle train_steps (float64) on the same batches."""
+    _torch()
+    pkg = package()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    tc = G.make_train_config(gradient_threshold=2.0, rules=rules, scale=0.05, momentum=0.5, decay_rate=0.95,
+                             epsilon=1e-6, max_norm=max_norm)
+    rec = make_recognizer(cfg, params)
+    algo = pkg.GradientDescent(recognizer=rec, step_rule=pkg.step_rule_from_config(tc, dict(max_norm=max_norm)))
+    algo.initialize()
+    ref = OrderedDict((k, v.copy()) for k, v in params.items())
+    state = {}
+    for step in range(2):
+        batch = O.synthetic_batch(cfg, B=4, T=40, seed=100 + step)
+        ref, ref_cost, ref_grads = G.train_step(cfg, ref, state, batch, tc)
+        algo.process_batch(dict(zip(algo.SOURCES, batch)))
+        assert abs(float(algo.last_cost.item()) - ref_cost) <= 1e-4 * abs(ref_cost)
+        assert abs(algo.total_gradient_norm() - G.l2_norm(ref_grads.values())) <= 1e-4 * G.l2_norm(ref_grads.values())
+        got = rec.get_parameter_values()
+        for k, v in ref.items():
+            # compare the UPDATE (new - old would cancel; the parameters themselves are O(0.1..1))
+            assert np.abs(got[k] - v).max() <= 2e-5 * max(1.0, np.abs(v).max()) + 1e-6, (step, k, np.abs(got[k] - v).max())
+    if max_norm > 0:
+        for k, v in rec.get_parameter_values().items():
+            if G.is_weight(k):
+                assert (np.sqrt((v.astype(np.float64) ** 2).sum(axis=0)) <= max_norm * (1 + 1e-5)).all(), k
+    # the forward pass uses the updated (re-packed) weights
+    x, m, labels, lm = O.synthetic_batch(cfg, B=3, T=32, seed=5)
+    want = O.recognizer_cost(cfg, ref, x, m, labels, lm)
+    got = rec.cost(x, m, labels, lm)
+    assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
+
+
+def test_non_finite_gradient_zeroes_the_parameter_and_burn_in_delays_updates():
+    torch = _torch()
+    pkg = package()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    batch = O.synthetic_batch(cfg, B=3, T=32, seed=1)
+    rec = make_recognizer(cfg, params)
+    algo = pkg.GradientDescent(recognizer=rec, step_rule=pkg.CompositeRule(
+        [pkg.StepClipping(10.0), pkg.Momentum(0.1, 0.0), pkg.RemoveNotFinite(0.0), pkg.BurnIn(num_steps=2)]))
+    algo.initialize()
+    before = rec.get_parameter_values()
+    for i in range(3):
+        algo.process_batch(dict(zip(algo.SOURCES, batch)))
+        after = rec.get_parameter_values()
+        changed = any(np.abs(after[k] - before[k]).max() > 0 for k in before)
+        assert changed == (i == 2), i              # lvsr/algorithms.py:35-43: the first num_steps updates are zeroed
+    # poison one gradient: RemoveNotFinite(0.0) zeroes that parameter, the others still move (B/algorithms/__init__.py:855-861)
+    x = batch[0].copy()
+    algo2 = pkg.GradientDescent(recognizer=rec, step_rule=pkg.CompositeRule([pkg.Momentum(0.1, 0.0), pkg.RemoveNotFinite(0.0)]))
+    algo2.initialize()
+    algo2._forward_backward(dict(zip(algo2.SOURCES, (x,) + tuple(batch[1:]))), None)
+    name = "/recognizer/generator/readout/post_merge/bias.b"
+    import ctypes as C
+    lib, h = pkg._lib.load(), rec._require_ready()
+    idx = list(rec.parameter_shapes()).index(name)
+    off, cnt = C.c_int64(), C.c_int64()
+    pkg._lib.check(lib.lvsr_model_param_offset(h, idx, C.byref(off), C.byref(cnt)))
+    algo2._buf[off.value] = float("nan")
+    pkg._lib.check(lib.lvsr_train_apply_updates(h, algo2._buf.data_ptr(), 1.0, C.byref(algo2._tc), rec._stream()))
+    torch.cuda.synchronize()
+    now = rec.get_parameter_values()
+    assert np.all(now[name] == 0)
+    other = "/recognizer/generator/readout/post_merge/mlp/linear_0.W"
+    assert np.abs(now[other] - after[other]).max() > 0 and np.isfinite(now[other]).all()
