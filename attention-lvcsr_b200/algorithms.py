@@ -158,6 +158,18 @@ def _to_train_config(step_rule, decay=0.0):
     return cfg
 
 
+def allreduce_step_buffer(buf, n, local_batch, local_cost, dist):
+    """The ONE collective of a data-parallel training step: sum over ranks of
+    [flat gradient (n floats) | local batch size | local cost sum].  ``buf`` is a 1-D float32 tensor of at
+    least n + 2 elements on any device ``dist`` can reduce (NCCL: the GPU buffer the backward pass wrote;
+    gloo: a CPU tensor in the host-side tests).  Returns (global batch size, global cost sum) as 0-d tensors
+    that live in ``buf`` -- reading them on the host synchronises."""
+    buf[n] = float(local_batch)
+    buf[n + 1:n + 2] = local_cost.reshape(1).to(buf.dtype) if hasattr(local_cost, "reshape") else float(local_cost)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf[n], buf[n + 1]
+
+
 class GradientDescent(object):
     """``GradientDescent(cost=..., parameters=..., step_rule=...)`` of the reference with the recognizer in
     place of the symbolic cost (there is no graph to differentiate: the backward pass is part of the library).
@@ -259,16 +271,13 @@ class GradientDescent(object):
             self.last_cost = self._cost                       # device scalar; .item() synchronises
             return
         B = self._forward_backward(batch, 1.0)                # gradient SUM over the local utterances
-        self._buf[self._n] = float(B)
-        self._buf[self._n + 1:self._n + 2] = self._cost
-        dist.all_reduce(self._buf, op=dist.ReduceOp.SUM)      # the ONE collective of the step
-        tail = self._buf[self._n:self._n + 2]
+        bg_dev, cost_dev = allreduce_step_buffer(self._buf, self._n, B, self._cost, dist)   # the ONE collective of the step
         # the global batch size has to reach the host to become a kernel argument; every rank knows its own B and
         # shards are equal-sized in the data-parallel loop, so the common case needs no synchronisation
-        Bg = B * world if self.equal_shards else int(round(float(tail[0].item())))
+        Bg = B * world if self.equal_shards else int(round(float(bg_dev.item())))
         _lib.check(lib.lvsr_train_apply_updates(h, self._buf.data_ptr(), 1.0 / Bg, C.byref(self._tc), rec._stream()))
         self.last_batch_size = Bg
-        self.last_cost = tail[1] / Bg
+        self.last_cost = cost_dev / Bg
 
     def total_gradient_norm(self):
         lib, h = _lib.load(), self.recognizer._require_ready()

@@ -178,6 +178,98 @@ def cpu_reference_run(steps, warmup, sample_B=16):
                "Theano CPU path (Theano itself cannot run: SURVEY.md 8c)" % (sample_B, W["T"], W["F"], W["L"]))
 
 
+TRAIN_WORKLOAD = dict(B=64, T=1500, F=40, L=190, V=32)       # BASELINE.json configs[3]
+TRAIN_CONF = dict(gradient_threshold=10.0, rules=["momentum", "adadelta"], scale=1.0, momentum=0.0, decay_rate=0.95,
+                  epsilon=1e-8)                              # exp/wsj/configs/wsj_jan_new.yaml:75-85
+TRAIN_METRIC = "training-step frames/sec at batch64x1500frx40fb (configs[3]: forward + backward + grad all-reduce + update)"
+
+
+def train_bench(pkg, torch, dev, rank, world, steps, warmup, dist_mod, flush, barrier):
+    """One training step = GradientDescent.process_batch on a synthetic config-4 batch per GPU: forward with tape,
+    BPTT, ONE NCCL all-reduce of the flat gradient buffer (N > 1), step rules + update.  Device time per step
+    (CUDA events, max over ranks), the all-reduce alone, and the same step from pinned host buffers."""
+    import ctypes as C
+    W = TRAIN_WORKLOAD
+    rec = pkg.SpeechRecognizer(
+        input_dims={"recordings": W["F"]}, input_num_chars={}, eos_label=W["V"] - 1, num_phonemes=W["V"],
+        dim_dec=NET["dim_dec"], dims_bidir=NET["dims_bidir"], subsample=NET["subsample"], conv_n=NET["conv_n"],
+        conv_num_filters=NET["conv_num_filters"], dim_matcher=NET["dim_matcher"],
+        post_merge_dims=NET["post_merge_dims"], post_merge_activation=pkg.Maxout(2),
+        enc_transition=pkg.GatedRecurrent, dec_transition=pkg.GatedRecurrent, device=dev)
+    rec.set_parameter_values(init_values(rec.parameter_shapes()))
+    algo = pkg.GradientDescent(recognizer=rec, step_rule=pkg.step_rule_from_config(TRAIN_CONF, dict(max_norm=1.0)))
+    algo.initialize()
+    lib = pkg._lib.load()
+    x, m, labels, lm = synthetic_batch(W["B"], W["T"], W["F"], W["L"], W["V"], seed=shard_seed(rank, base=4321))
+    names = ("recordings", "recordings_mask", "labels", "labels_mask")
+    dbatch = dict(zip(names, (torch.as_tensor(a, device=dev) for a in (x, m, labels, lm))))
+    hbatch = dict(zip(names, (torch.as_tensor(a).pin_memory() for a in (x, m, labels, lm))))
+    for _ in range(max(2, warmup)):
+        algo.process_batch(dbatch)
+    barrier()
+    lib.lvsr_launch_count(1)
+    total_ms = 0.0
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        algo.process_batch(dbatch)
+        b.record()
+        torch.cuda.synchronize(dev)
+        total_ms += a.elapsed_time(b)
+    launches = int(lib.lvsr_launch_count(1))
+    ms_dev = max_over_ranks(total_ms, world, dev, dist_mod) / steps
+    cost = float(algo.last_cost.item())
+    # the collective alone
+    ar_ms = 0.0
+    if world > 1:
+        buf = torch.zeros_like(algo._buf)
+        for _ in range(2):
+            dist_mod.all_reduce(buf)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            dist_mod.all_reduce(buf)
+        b.record()
+        torch.cuda.synchronize(dev)
+        ar_ms = max_over_ranks(a.elapsed_time(b), world, dev, dist_mod) / steps
+    # end to end from pinned host buffers, cost read back every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        algo.process_batch({k: v.to(dev, non_blocking=True) for k, v in hbatch.items()})
+        cost = float(algo.last_cost.item())
+    ms_host = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev, dist_mod) / steps
+    barrier()
+    prof = {}
+    lib.lvsr_profile_enable(1)
+    algo.process_batch(dbatch)
+    torch.cuda.synchronize(dev)
+    for cls in ("gemm", "gemm_tn", "bigru", "bigru_bwd", "dec_scan", "dec_bwd_step", "readout"):
+        tot, cnt = C.c_double(), C.c_int64()
+        lib.lvsr_profile_read(cls.encode(), C.byref(tot), C.byref(cnt))
+        prof[cls] = {"ms": round(tot.value, 3), "launches": cnt.value}
+    lib.lvsr_profile_enable(0)
+    frames = W["B"] * W["T"] * world
+    return {
+        "metric": TRAIN_METRIC, "value": frames / (ms_dev * 1e-3), "unit": "frames/s", "ms_per_step": ms_dev,
+        "n_gpus": world, "steps": steps, "scaling": "weak", "dtype": "f32",
+        "config": {"workload": "configs[3]: batch %d x %d frames x %d fbank per GPU, WSJ architecture, %d label steps, "
+                               "StepClipping(10) + Momentum(1, 0) + AdaDelta(0.95, 1e-8) + max-norm 1 (wsj_jan_new.yaml)"
+                               % (W["B"], W["T"], W["F"], W["L"]),
+                   "global_batch": W["B"] * world, "parallelism": "dp%d, one all-reduce(sum) of the flat gradient buffer per step" % world},
+        "e2e": {"value": frames / (ms_host * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": int(x.nbytes + m.nbytes + labels.nbytes + lm.nbytes), "d2h_bytes_per_step": 4},
+        "collective": {"kind": "NCCL all-reduce(sum), fp32" if world > 1 else "none (1 GPU)",
+                       "bytes": int(algo._buf.numel() * 4), "ms_alone": ar_ms,
+                       "share_of_step": (ar_ms / ms_dev) if ms_dev > 0 else None},
+        "gpu_launches_per_step": launches // max(1, steps),
+        "kernel_ms_per_step": prof, "cost": cost,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +277,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="metric", choices=["metric", "train"],
+                    help="metric: the BASELINE headline (forward cost, teacher forcing) with a `train` block for the "
+                         "training step; train: the training step (configs[3]) as the main line")
+    ap.add_argument("--no-train", action="store_true", help="metric mode: skip the training-step block")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"],
                     help="diagnostic only: utterances per GPU (the metric is quoted on the default)")
     args = ap.parse_args()
@@ -270,6 +366,20 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
 
+    if args.mode == "train":
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        tr = train_bench(pkg, torch, dev, rank, world, args.steps, args.warmup, dist_mod, flush, barrier)
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        if rank == 0:
+            tr.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic",
+                       "gpu_launches": tr["gpu_launches_per_step"] * args.steps, "clocks": sampler.summary()})
+            print(json.dumps(tr))
+        if world > 1:
+            dist_mod.destroy_process_group()
+        return 0
+
     for _ in range(args.warmup):
         step_device()
     step_host()
@@ -307,7 +417,16 @@ def main():
         prof[cls] = {"ms": tot.value, "launches": cnt.value}
     lib.lvsr_profile_enable(0)
 
+    train_block = None
+    if not args.no_train and args.batch == WORKLOAD["B"]:
+        try:
+            train_block = train_bench(pkg, torch, dev, rank, world, max(2, min(args.steps, 5)), 2, dist_mod, flush, barrier)
+        except Exception as e:          # the headline must survive a failure of the secondary measurement
+            train_block = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
+        if world > 1:
+            dist_mod.destroy_process_group()
         return 0
 
     frames = W["B"] * W["T"] * world
@@ -370,6 +489,8 @@ def main():
         "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "kernel_launches_per_step": {k: v["launches"] for k, v in prof.items()},
     }
+    if train_block is not None:
+        out["train"] = train_block
     if not args.no_cpu_baseline:
         _, _, cb = cpu_reference_run(1, 0)
         out["cpu_baseline"] = cb

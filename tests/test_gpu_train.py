@@ -147,3 +147,20 @@ def test_non_finite_gradient_zeroes_the_parameter_and_burn_in_delays_updates():
     assert np.all(now[name] == 0)
     other = "/recognizer/generator/readout/post_merge/mlp/linear_0.W"
     assert np.abs(now[other] - after[other]).max() > 0 and np.isfinite(now[other]).all()
+
+
+def test_two_gpu_step_equals_single_gpu_step_on_the_concatenated_batch():
+    """batch sharded over ranks + ONE NCCL all-reduce of the flat gradient buffer."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tests", "dist_train_worker.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "DIST_TRAIN_OK" in r.stdout
