@@ -121,13 +121,16 @@ int copy_cols(float* dst, int ld_dst, int col0, const float* src, int rows, int 
 
 
 // take_glimpses for R rows: q = s.W_state, window, attention step.
+struct Segments {           // batched beam search: hypotheses of one utterance = one segment (the reference's batch)
+  const int* seg_start = nullptr; int nseg = 0; const int* seg_len = nullptr; const int* row_seg = nullptr;
+};
 int glimpses(lvsr_model* m, const float* H, const float* P, const float* maskH, int Tp, int U,
              const int* row_utt, int R, const float* states, const float* w_prev, const long long* step,
-             long long step_offset, float* w_out, float* e_out, float* ctx, cudaStream_t st) {
+             long long step_offset, float* w_out, float* e_out, float* ctx, cudaStream_t st, Segments sg = Segments()) {
   const lvsr_config& c = m->cfg;
   Arena& ws = m->ws;
   float* q = ws.f32((size_t)R * c.dim_matcher);
-  int* win = ws.i32(2);
+  int* win = ws.i32((size_t)2 * std::max(1, sg.nseg));
   float* lohi = ws.f32((size_t)2 * R);
   LVSR_CHECK(q && win && lohi, "out of device memory (workspace)");
   DenseArgs d = {};
@@ -137,9 +140,11 @@ int glimpses(lvsr_model* m, const float* H, const float* P, const float* maskH, 
   WindowArgs wa = {};
   wa.weights = w_prev; wa.step = step; wa.step_offset = step_offset; wa.R = R; wa.Tp = Tp;
   wa.prior = prior_of(c); wa.win = win; wa.lohi = lohi;
+  wa.seg_start = sg.seg_start; wa.nseg = sg.nseg; wa.seg_len = sg.seg_len;
   if (int rc = attention_window(wa, st)) return rc;
   AttStepArgs a = {};
   a.P = P; a.H = H; a.maskH = maskH; a.row_utt = row_utt; a.q = q; a.w_prev = w_prev; a.win = win; a.lohi = lohi;
+  a.row_seg = sg.seg_start ? sg.row_seg : nullptr;
   a.filt = m->P(std::string(ATT) + "/conv1d.filters");
   a.Wh = m->P(std::string(ATT) + "/handler.W");
   a.v = m->P(std::string(ATT) + "/energy_comp/linear.W");
@@ -819,6 +824,80 @@ int lvsr_next_states(lvsr_model* m, const float* attended, const float* preproce
                         reinterpret_cast<const long long*>(step), 0, next_weights, next_energies, next_wavg, st)) return rc;
   if (int rc = transition(m, R, states, next_wavg, reinterpret_cast<const long long*>(outputs), nullptr, next_states, st)) return rc;
   return add_i64(reinterpret_cast<long long*>(next_step), reinterpret_cast<const long long*>(step), R, 1, st);
+}
+
+int lvsr_search_expand(lvsr_model* m, const float* attended, const float* preprocessed, const float* attended_mask,
+                       int32_t Tp, int32_t U, const int32_t* utt_len, const int32_t* row_utt, const int32_t* row_seg,
+                       const int32_t* seg_start, int32_t nseg, int32_t R, const float* states, const float* weights,
+                       const int64_t* step, const float* cost_so_far, int32_t k, float* wavg, float* new_weights,
+                       float* new_energies, int32_t* top_parent, int32_t* top_symbol, float* top_cost, int32_t* top_count,
+                       void* stream) {
+  DeviceGuard device_guard(m);
+  if (int rc = check_ready(m)) return rc;
+  LVSR_CHECK(attended && preprocessed && attended_mask && row_utt && row_seg && seg_start && states && weights && step &&
+                 cost_so_far && wavg && new_weights && new_energies && top_parent && top_symbol && top_cost && top_count &&
+                 Tp > 0 && U > 0 && nseg > 0 && R > 0 && k > 0,
+             "search_expand: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ArenaScope scope(m, st);
+  const lvsr_config& c = m->cfg;
+  Arena& ws = m->ws;
+  float* merged = ws.f32((size_t)R * c.post_merge_dim);
+  float* neglogp = ws.f32((size_t)R * c.num_phonemes);
+  LVSR_CHECK(merged && neglogp, "out of device memory (search workspace)");
+  Segments sg;
+  sg.seg_start = seg_start; sg.nseg = nseg; sg.seg_len = utt_len; sg.row_seg = row_seg;
+  // take_glimpses ONCE per hypothesis: the same glimpse feeds the readout (logprobs_computer) and, for the
+  // surviving parents, the state update (next_state_computer) -- B/search.py:109-142 computes it twice
+  if (int rc = glimpses(m, attended, preprocessed, attended_mask, Tp, U, row_utt, R, states, weights,
+                        reinterpret_cast<const long long*>(step), 0, new_weights, new_energies, wavg, st, sg)) return rc;
+  if (int rc = readout_merged(m, R, states, wavg, merged, st)) return rc;
+  ReadoutArgs r = readout_args(m, R, merged);
+  r.costs_all = neglogp;
+  if (int rc = readout_costs(r, st)) return rc;
+  return segment_topk(neglogp, cost_so_far, seg_start, nseg, c.num_phonemes, k, top_parent, top_symbol, top_cost, top_count, st);
+}
+
+int lvsr_search_advance(lvsr_model* m, const float* attended, const float* preprocessed, const float* attended_mask,
+                        int32_t Tp, int32_t U, const int32_t* utt_len, int32_t Rn, const int32_t* parent,
+                        const int64_t* symbols, const int32_t* row_utt, const int32_t* row_seg, const int32_t* seg_start,
+                        int32_t nseg, const float* states, const float* weights, const int64_t* step, const float* wavg,
+                        const float* new_weights, const float* new_energies, int32_t reuse_glimpses, float* n_states,
+                        float* n_wavg, float* n_weights, float* n_energies, int64_t* n_step, void* stream) {
+  DeviceGuard device_guard(m);
+  if (int rc = check_ready(m)) return rc;
+  LVSR_CHECK(parent && symbols && states && step && n_states && n_wavg && n_weights && n_energies && n_step && Rn > 0 && Tp > 0,
+             "search_advance: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ArenaScope scope(m, st);
+  const lvsr_config& c = m->cfg;
+  Arena& ws = m->ws;
+  const int C = c.dim_dec, E = m->E;
+  float* s_sel = ws.f32((size_t)Rn * C);
+  LVSR_CHECK(s_sel, "out of device memory (search workspace)");
+  if (int rc = gather_rows(s_sel, states, parent, Rn, C, st)) return rc;
+  if (reuse_glimpses) {
+    LVSR_CHECK(wavg && new_weights && new_energies, "search_advance: glimpses of the parents are missing");
+    if (int rc = gather_rows(n_wavg, wavg, parent, Rn, E, st)) return rc;
+    if (int rc = gather_rows(n_weights, new_weights, parent, Rn, Tp, st)) return rc;
+    if (int rc = gather_rows(n_energies, new_energies, parent, Rn, Tp, st)) return rc;
+  } else {
+    // window priors: the reference recomputes the glimpses over the SELECTED parents, whose batch-global cut
+    // (lvsr/bricks/attention.py:151-152) can differ from the cut over the whole beam
+    LVSR_CHECK(attended && preprocessed && attended_mask && row_utt && row_seg && seg_start && weights && nseg > 0,
+               "search_advance: contexts are required to recompute the glimpses");
+    float* w_sel = ws.f32((size_t)Rn * Tp);
+    long long* st_sel = ws.i64((size_t)Rn);
+    LVSR_CHECK(w_sel && st_sel, "out of device memory (search workspace)");
+    if (int rc = gather_rows(w_sel, weights, parent, Rn, Tp, st)) return rc;
+    if (int rc = gather_i64(st_sel, reinterpret_cast<const long long*>(step), parent, Rn, 0, st)) return rc;
+    Segments sg;
+    sg.seg_start = seg_start; sg.nseg = nseg; sg.seg_len = utt_len; sg.row_seg = row_seg;
+    if (int rc = glimpses(m, attended, preprocessed, attended_mask, Tp, U, row_utt, Rn, s_sel, w_sel, st_sel, 0, n_weights,
+                          n_energies, n_wavg, st, sg)) return rc;
+  }
+  if (int rc = transition(m, Rn, s_sel, n_wavg, reinterpret_cast<const long long*>(symbols), nullptr, n_states, st)) return rc;
+  return gather_i64(reinterpret_cast<long long*>(n_step), reinterpret_cast<const long long*>(step), parent, Rn, 1, st);
 }
 
 int lvsr_recognizer_cost_host(lvsr_model* m, const float* x_h, const float* mask_h, const int64_t* labels_h,

@@ -26,29 +26,32 @@ constexpr int ATT_THREADS = ATT_NT;
 __global__ void __launch_bounds__(256) window_kernel(WindowArgs a) {
   __shared__ float s_lo[8], s_hi[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Tp = a.Tp;
+  const int sg = blockIdx.x;                              // one CTA per segment
+  const int r_begin = a.seg_start ? a.seg_start[sg] : 0, r_end = a.seg_start ? a.seg_start[sg + 1] : a.R;
+  const int Tp = a.Tp;                                    // row pitch of the weights
+  const int Tl = a.seg_len ? a.seg_len[sg] : Tp;          // `length` of the reference: the utterance's own encoded length
   if (a.prior.type == LVSR_PRIOR_EXPANDING) {
-    // lvsr/bricks/attention.py:127-132 -- step[0] decides for the whole batch
+    // lvsr/bricks/attention.py:127-132 -- step[0] (first row of the batch) decides for the whole batch
     if (tid == 0) {
-      const double st = (double)((a.step ? a.step[0] : 0LL) + a.step_offset);
+      const double st = (double)((a.step ? a.step[r_begin] : 0LL) + a.step_offset);
       double begin = a.prior.initial_begin + st * a.prior.min_speed;
       double end = a.prior.initial_end + st * a.prior.max_speed;
-      begin = fmax(0.0, fmin((double)(Tp - 1), begin));
-      end = fmax(0.0, fmin((double)Tp, end));
-      a.win[0] = (int)floor(begin);
-      a.win[1] = (int)ceil(end);
+      begin = fmax(0.0, fmin((double)(Tl - 1), begin));
+      end = fmax(0.0, fmin((double)Tl, end));
+      a.win[2 * sg] = (int)floor(begin);
+      a.win[2 * sg + 1] = (int)ceil(end);
     }
-    for (int r = tid; r < a.R; r += blockDim.x) {
+    for (int r = r_begin + tid; r < r_end; r += blockDim.x) {
       a.lohi[2 * r] = -1e30f;
       a.lohi[2 * r + 1] = 1e30f;
     }
     return;
   }
   float my_lo = 1e30f, my_hi = -1e30f;
-  const int chunk = (Tp + 31) / 32;
-  for (int r = warp; r < a.R; r += 8) {
+  const int chunk = (Tl + 31) / 32;
+  for (int r = r_begin + warp; r < r_end; r += 8) {
     const float* w = a.weights + (long long)r * Tp;
-    const int i0 = lane * chunk, i1 = min(Tp, i0 + chunk);
+    const int i0 = lane * chunk, i1 = min(Tl, i0 + chunk);
     double pos;
     if (a.prior.type == LVSR_PRIOR_WINDOW_MEAN) {
       double acc = 0.0;                                   // :136-137
@@ -91,8 +94,8 @@ __global__ void __launch_bounds__(256) window_kernel(WindowArgs a) {
   if (tid == 0) {
     float lo = s_lo[0], hi = s_hi[0];
     for (int i = 1; i < 8; ++i) { lo = fminf(lo, s_lo[i]); hi = fmaxf(hi, s_hi[i]); }
-    a.win[0] = (int)fmaxf(0.f, lo);                         // :149-150
-    a.win[1] = (int)fminf((float)Tp, hi);
+    a.win[2 * sg] = (int)fmaxf(0.f, lo);                    // :149-150
+    a.win[2 * sg + 1] = (int)fminf((float)Tl, hi);
   }
 }
 
@@ -118,7 +121,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) att_step_kernel(AttStepArgs a,
   io.ctx_out = a.ctx + (long long)row * a.E;
   io.u = a.row_utt ? a.row_utt[row] : row;
   io.U = a.U; io.Tp = a.Tp; io.M = a.M; io.E = a.E; io.K = a.K; io.n = a.n; io.normalizer = a.normalizer;
-  io.b0 = a.win[0]; io.b1 = a.win[1];
+  const int sg = a.row_seg ? a.row_seg[row] : 0;
+  io.b0 = a.win[2 * sg]; io.b1 = a.win[2 * sg + 1];
   io.lo = a.lohi[2 * row]; io.hi = a.lohi[2 * row + 1];
   attention_row(io, smem, tc_cap, rank, cs, false, false, true);
 }
@@ -156,7 +160,7 @@ int launch_att(const AttStepArgs& a, int cs, cudaStream_t stream) {
 
 int attention_window(const WindowArgs& a, cudaStream_t stream) {
   ProfScope prof("window", stream);
-  window_kernel<<<1, 256, 0, stream>>>(a);
+  window_kernel<<<a.seg_start ? a.nseg : 1, 256, 0, stream>>>(a);
   LVSR_LAUNCH_CHECK();
   return 0;
 }

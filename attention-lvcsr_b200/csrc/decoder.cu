@@ -202,6 +202,70 @@ __global__ void count_sentinels_kernel(const unsigned* p, long long n, unsigned 
   if (c) atomicAdd(out, c);
 }
 
+__global__ void gather_rows_kernel(float* dst, const float* src, const int* idx, long long total, int N) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[(long long)idx[i / N] * N + i % N];
+}
+__global__ void gather_i64_kernel(long long* dst, const long long* src, const int* idx, int n, long long inc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]] + inc;
+}
+
+// BeamSearch._smallest (B/search.py:220-242) for every utterance of a batched search: the k smallest entries of
+// cost_so_far[r] + neglogp[r, v] over the segment's rows, in increasing order (ties: smaller flat index first).
+// One CTA per segment; the candidate table (width x V <= k x 128 floats) lives in shared memory and k rounds of a
+// block-wide arg-min pick the winners.  top_count = -1 flags a non-finite log-probability (the reference asserts).
+__global__ void __launch_bounds__(256) segment_topk_kernel(const float* neglogp, const float* cost_so_far, const int* seg_start,
+                                                           int V, int k, int* top_parent, int* top_symbol, float* top_cost,
+                                                           int* top_count) {
+  extern __shared__ float cand[];
+  __shared__ float rv[8];
+  __shared__ int ri[8];
+  __shared__ int bad;
+  const int sg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = seg_start[sg], width = seg_start[sg + 1] - r0, n = width * V;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const float lp = neglogp[(long long)r0 * V + i];
+    if (!isfinite(lp)) bad = 1;
+    cand[i] = cost_so_far[r0 + i / V] + lp;
+  }
+  __syncthreads();
+  const int take = min(k, n);
+  for (int round = 0; round < take; ++round) {
+    float bv = INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < n; i += 256) {
+      const float v = cand[i];
+      if (v < bv) { bv = v; bi = i; }           // strided scan keeps the smallest index among equal values per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 1; q < 8; ++q)
+        if (rv[q] < rv[0] || (rv[q] == rv[0] && ri[q] < ri[0])) { rv[0] = rv[q]; ri[0] = ri[q]; }
+      const int idx = ri[0];
+      if (idx != 0x7fffffff) {
+        top_parent[sg * k + round] = r0 + idx / V;
+        top_symbol[sg * k + round] = idx % V;
+        top_cost[sg * k + round] = rv[0];
+        cand[idx] = INFINITY;
+      } else {                                  // every remaining candidate is +inf / NaN
+        top_parent[sg * k + round] = -1;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) top_count[sg] = bad ? -1 : take;
+}
+
 inline int grid_for(long long n) { return (int)std::min<long long>(2048, std::max<long long>(1, (n + 255) / 256)); }
 
 }  // namespace
@@ -266,6 +330,34 @@ int count_sentinels(const float* p, long long n, long long* host_count, cudaStre
   cudaFree(d);
   if (e != cudaSuccess) return set_error("count_sentinels failed: %s", cudaGetErrorString(e));
   *host_count = (long long)h;
+  return 0;
+}
+int gather_rows(float* dst, const float* src, const int* idx, int Rn, int N, cudaStream_t stream) {
+  const long long total = (long long)Rn * N;
+  if (total <= 0) return 0;
+  gather_rows_kernel<<<grid_for(total), 256, 0, stream>>>(dst, src, idx, total, N);
+  LVSR_LAUNCH_CHECK();
+  return 0;
+}
+int gather_i64(long long* dst, const long long* src, const int* idx, int Rn, long long inc, cudaStream_t stream) {
+  if (Rn <= 0) return 0;
+  gather_i64_kernel<<<ceil_div(Rn, 256), 256, 0, stream>>>(dst, src, idx, Rn, inc);
+  LVSR_LAUNCH_CHECK();
+  return 0;
+}
+int segment_topk(const float* neglogp, const float* cost_so_far, const int* seg_start, int nseg, int V, int k,
+                 int* top_parent, int* top_symbol, float* top_cost, int* top_count, cudaStream_t stream) {
+  if (nseg <= 0) return 0;
+  const size_t smem = (size_t)k * V * sizeof(float);        // a segment never holds more than k rows
+  LVSR_CHECK(smem <= 200 * 1024, "beam search: beam_size %d x %d symbols does not fit the selection kernel", k, V);
+  static size_t configured[LVSR_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (smem > configured[dev] && smem > 48 * 1024) {
+    LVSR_CUDA_OK(cudaFuncSetAttribute(segment_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = smem;
+  }
+  segment_topk_kernel<<<nseg, 256, smem, stream>>>(neglogp, cost_so_far, seg_start, V, k, top_parent, top_symbol, top_cost, top_count);
+  LVSR_LAUNCH_CHECK();
   return 0;
 }
 int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream) {

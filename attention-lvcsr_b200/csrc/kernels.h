@@ -79,8 +79,13 @@ struct WindowArgs {
   long long step_offset;   // added to step[0] (teacher forcing: the step index)
   int R, Tp;
   PriorParams prior;
-  int* win;                // [2]
+  int* win;                // [2] (or [2 * nseg])
   float* lohi;             // [2R]
+  // optional segmentation (batched beam search: one segment = the hypotheses of one utterance, which is the
+  // reference's "batch" for the batch-global cut): rows [seg_start[s], seg_start[s+1]) -> win[2s], win[2s+1]
+  const int* seg_start;    // [nseg + 1] or nullptr (one segment = all rows)
+  int nseg;
+  const int* seg_len;      // [nseg] valid encoded frames of the segment's utterance (<= Tp) or nullptr (= Tp)
 };
 int attention_window(const WindowArgs& a, cudaStream_t stream);
 
@@ -91,7 +96,8 @@ struct AttStepArgs {
   const int* row_utt;      // [R] or nullptr (identity)
   const float* q;          // [R, M]  states . W_state
   const float* w_prev;     // [R, Tp]
-  const int* win;          // [2] from attention_window
+  const int* win;          // [2] from attention_window ([2 * nseg] with row_seg)
+  const int* row_seg;      // [R] segment of each row or nullptr (all rows share win[0..1])
   const float* lohi;       // [2R]
   const float* filt;       // [K, 2n+1]
   const float* Wh;         // [K, M]
@@ -179,6 +185,11 @@ int fill_i64(long long* p, long long n, long long v, cudaStream_t stream);
 int broadcast_rows(float* dst, const float* src, int R, int N, cudaStream_t stream);   // dst[r,:] = src[:]
 int onehot_rows(float* dst, int R, int N, cudaStream_t stream);                         // dst[r,:] = e_0
 int count_sentinels(const float* p, long long n, long long* host_count, cudaStream_t stream);   // synchronises
+int gather_rows(float* dst, const float* src, const int* idx, int Rn, int N, cudaStream_t stream);   // dst[r,:] = src[idx[r],:]
+int gather_i64(long long* dst, const long long* src, const int* idx, int Rn, long long inc, cudaStream_t stream);
+// k smallest of cost_so_far[r] + neglogp[r, v] over the rows of each segment (B/search.py:341-344)
+int segment_topk(const float* neglogp, const float* cost_so_far, const int* seg_start, int nseg, int V, int k,
+                 int* top_parent, int* top_symbol, float* top_cost, int* top_count, cudaStream_t stream);
 int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream);
 int gather_time_subsample(float* dst, const float* src, int Tout, int k, long long row_elems,
                           cudaStream_t stream);                                         // dst[t] = src[t*k]

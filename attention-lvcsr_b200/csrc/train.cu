@@ -86,6 +86,7 @@ int skinny(const float* X0, int K0, int ldx0, const float* W0, const float* X1, 
   a.add[0] = add0; a.lda[0] = lda0; a.add[1] = add1; a.lda[1] = lda1;
   a.out = out; a.ldo = ldo; a.R = R; a.N = N;
   dim3 grid(ceil_div(N, SK_N), ceil_div(R, SK_R));
+  ProfScope prof("skinny", st);
   skinny_kernel<<<grid, 256, 0, st>>>(a);
   LVSR_LAUNCH_CHECK();
   return 0;
@@ -342,8 +343,11 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       ab.dP = dP; ab.dq_part = dQp + (size_t)i * 2 * B * M; ab.dA_out = dAbuf[(L - i) & 1];
       ab.acc_v = acc_v; ab.acc_Wh = acc_Wh; ab.acc_filt = acc_filt;
       ab.B = B; ab.Tp = Tp; ab.M = M; ab.E = E; ab.K = K; ab.n = n;
-      att_bwd_kernel<<<nct, AB_NT, ab_smem, st>>>(ab, tc_cap);
-      LVSR_LAUNCH_CHECK();
+      {
+        ProfScope prof_ab("att_bwd", st);
+        att_bwd_kernel<<<nct, AB_NT, ab_smem, st>>>(ab, tc_cap);
+        LVSR_LAUNCH_CHECK();
+      }
       // ds_{i-1} = gates/elementwise part + dq . W_s^T (two partials) + readout of step i (which saw s_{i-1})
       const float* q0 = dQp + (size_t)i * 2 * B * M;
       if (int rc = skinny(q0, M, M, WsT, q0 + (size_t)B * M, M, M, WsT, dspart, C, dS_ro + (size_t)i * B * C, C, ds_next, C, B, C, st)) return rc;

@@ -436,6 +436,21 @@ class SpeechRecognizer(object):
         return self._beam_search.search({"recordings": rec[:, None, :]}, self.eos_label, max_length,
                                         ignore_first_eol=self.data_prepend_eos, **kwargs)
 
+    def beam_search_many(self, inputs_list, **kwargs):
+        """beam_search for a list of {'recordings': [T_u, F]} decoded together on the GPU (one set of launches per
+        step for all utterances, BeamSearch.search_many); returns [(outputs, costs), ...] in order.  The
+        reference decodes one utterance at a time (lvsr/main.py:806-821 loops over the data stream)."""
+        self.init_beam_search(self.beam_size)
+        recs = []
+        for inputs in inputs_list:
+            inputs = dict(inputs)
+            recs.append(np.asarray(inputs.pop("recordings"), dtype=np.float32))
+            if inputs:
+                raise Exception("Unknown inputs passed to beam search: {}".format(list(inputs.keys())))
+        max_lengths = [int(x.shape[0] / self.max_decoded_length_scale) for x in recs]
+        return self._beam_search.search_many(recs, self.eos_label, max_lengths,
+                                             ignore_first_eol=self.data_prepend_eos, **kwargs)
+
     # ------------------------------------------------------------------------------
     # BeamSearch state functions (C-ABI calls)
     # ------------------------------------------------------------------------------

@@ -4,12 +4,18 @@ Same constructor/driver contract as the reference's (modified) class
 (libs/blocks/blocks/search.py:19-407): ``BeamSearch(beam_size, recognizer)``,
 ``compile()``, ``search(input_values, eol_symbol, max_length, ...)`` returning
 ``(outputs, costs)``.  The four compiled Theano functions become four C-ABI calls
-(lvsr_encoder_forward, lvsr_initial_states, lvsr_logprobs, lvsr_next_states); all
-hypothesis state stays on the GPU between steps, only the [width, V] cost table
-crosses to the host for the k-best selection.  Differences from the reference that
-do not change results: the encoded sequence is NOT replicated per hypothesis (rows
-index their utterance) and attention.preprocess runs once per utterance instead of
-twice per step.
+(lvsr_encoder_forward, lvsr_initial_states, lvsr_logprobs, lvsr_next_states) for the
+state functions, and the search loop itself runs on ``lvsr_search_expand`` /
+``lvsr_search_advance``: all hypothesis state stays on the GPU, the k-best selection
+(``_smallest``) happens on the GPU, and only k (parent, symbol, cost) triples per utterance
+cross to the host each step, where the reference's bookkeeping (histories, ``done`` list,
+stopping criteria, B/search.py:306-377) runs unchanged.  ``search_many`` decodes MANY
+utterances in lock-step with one set of launches per step (rows index their utterance;
+the batch-global window cut of take_glimpses is taken per utterance, exactly as if each
+were decoded alone).  Differences from the reference that do not change results: the encoded
+sequence is NOT replicated per hypothesis, attention.preprocess runs once per utterance
+instead of twice per step, and with the expanding prior the glimpse computed for the
+log-probabilities is reused for the state update instead of being recomputed.
 """
 import numpy as np
 
@@ -68,90 +74,201 @@ class BeamSearch(object):
                char_discount=0, round_to_inf=1e9, stop_on="patience", validate_solution_function=None):
         """See the reference docstring (libs/blocks/blocks/search.py:244-288).
         ``input_values``: {'recordings': array [T, 1, F]} (name or any single key)."""
+        (recordings,) = list(input_values.values())
+        rec = np.asarray(recordings.cpu() if hasattr(recordings, "cpu") else recordings, dtype=np.float32)
+        if rec.ndim != 3 or rec.shape[1] != 1:
+            raise ValueError("search expects recordings [T, 1, F]")
+        res = self.search_many([rec[:, 0, :]], eol_symbol, [max_length], ignore_first_eol=ignore_first_eol,
+                               as_arrays=as_arrays, char_discount=char_discount, round_to_inf=round_to_inf,
+                               stop_on=stop_on, validate_solution_function=validate_solution_function,
+                               input_values=[input_values])
+        return res[0]
+
+    def search_many(self, recordings_list, eol_symbol, max_lengths, ignore_first_eol=False, as_arrays=False,
+                    char_discount=0, round_to_inf=1e9, stop_on="patience", validate_solution_function=None,
+                    input_values=None, raise_on_failure=True):
+        """BeamSearch.search (B/search.py:244-399) for a list of utterances [T_u, F] decoded in lock-step.
+        Returns one result per utterance (same format as ``search``); an utterance without a finished
+        hypothesis raises CandidateNotFoundError (or yields None with raise_on_failure=False)."""
+        import ctypes as C
         import torch
+        if stop_on not in ("patience", "optimistic_future_cost"):
+            raise ValueError("Unknown stopping criterion {}".format(stop_on))
         if not self.compiled:
             self.compile()
-        (recordings,) = list(input_values.values())
-        contexts = self.compute_contexts(recordings)
-        states = self.compute_initial_states(contexts)
+        r = self.recognizer
+        lib, h = _lib.load(), r._require_ready()
+        dev = r.device
+        k = int(self.beam_size)
+        U = len(recordings_list)
+        if U == 0:
+            return []
+        lens = [int(x.shape[0]) for x in recordings_list]
+        Tmax, F = max(lens), int(recordings_list[0].shape[1])
+        x = np.zeros((Tmax, U, F), dtype=np.float32)
+        for u, a in enumerate(recordings_list):
+            x[:lens[u], u, :] = np.asarray(a, dtype=np.float32)
+        mask = None
+        if min(lens) != Tmax:
+            mask = (np.arange(Tmax)[:, None] < np.asarray(lens)[None, :]).astype(np.float32)
+        # one encoder pass for all utterances; right-padding is exact under the mask (the masked GRU step returns
+        # the carried state bit for bit) and every utterance attends over its own encoded length only
+        att, attm = r.encode(x, mask)
+        P = r.preprocess(att)
+        Tp = int(att.shape[0])
+        enc_len = np.asarray([r.encoded_length(t) for t in lens], dtype=np.int32)
+        reuse = 1 if r.net["prior"].get("type", "expanding") == "expanding" else 0
+        st = r._initial_states(Tp, U)
+        states, weights, step = st["states"], st["weights"], st["step"]
 
-        outputs_hist = states["outputs"].cpu().numpy()[None, :]       # includes the initial symbol
-        costs_hist = np.zeros(outputs_hist.shape, dtype=np.float32)
-        done = []
-        min_cost = 1000
-        patience = None
+        utts = []
+        for u in range(U):
+            utts.append(dict(outputs=np.full((1, 1), r.net["num_phonemes"], dtype=np.int64),   # initial symbol, recognizer.py:286
+                             costs=np.zeros((1, 1), dtype=np.float32), done=[], min_cost=1000, patience=None,
+                             max_length=int(max_lengths[u]), active=True))
+        order = list(range(U))            # utterances that own rows, in row order (one segment each)
 
         def discounted(item):
             return item[1][-1] - char_discount * len(item[1])
 
-        for i in range(max_length):
-            if states["states"].shape[0] == 0:
+        def i32(a):
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+
+        V = r.net["num_phonemes"]
+        for i in range(max(int(m) for m in max_lengths) if U else 0):
+            # ---- top of the reference loop, per utterance: length limit, empty beam, stopping criterion ----
+            keep_rows, new_order, row0 = [], [], 0
+            for u in order:
+                ut = utts[u]
+                width = ut["outputs"].shape[1]
+                stop = i >= ut["max_length"] or width == 0
+                if not stop and stop_on == "patience":
+                    ut["done"] = sorted(ut["done"], key=discounted)[:k]
+                    if ut["done"]:
+                        best = discounted(ut["done"][0])
+                        if best < ut["min_cost"]:
+                            ut["min_cost"], ut["patience"] = best, 30
+                        else:
+                            ut["patience"] -= 1
+                            stop = ut["patience"] == 0
+                elif not stop and stop_on == "optimistic_future_cost":
+                    if len(ut["done"]) >= k:
+                        optimistic = ut["costs"][-1, :].min() - char_discount * ut["max_length"]
+                        last = ut["done"][k - 1][1]
+                        stop = last[-1] - char_discount * len(last) < optimistic
+                if stop:
+                    ut["active"] = False
+                else:
+                    new_order.append(u)
+                    keep_rows.extend(range(row0, row0 + width))
+                row0 += width
+            if len(keep_rows) != row0:
+                if not keep_rows:
+                    break
+                sel = torch.as_tensor(np.asarray(keep_rows, dtype=np.int64), device=dev)
+                states, weights, step = states.index_select(0, sel), weights.index_select(0, sel), step.index_select(0, sel)
+            order = new_order
+            if not order:
                 break
-            if stop_on == "patience":
-                done = sorted(done, key=discounted)[:self.beam_size]
-                if done:
-                    best = discounted(done[0])
-                    if best < min_cost:
-                        min_cost, patience = best, 30
-                    else:
-                        patience -= 1
-                        if patience == 0:
-                            break
-            elif stop_on == "optimistic_future_cost":
-                if len(done) >= self.beam_size:
-                    optimistic = costs_hist[-1, :].min() - char_discount * max_length
-                    last = done[self.beam_size - 1][1]
-                    if last[-1] - char_discount * len(last) < optimistic:
-                        break
+            # ---- one expand for every live hypothesis of every utterance ----
+            widths = [utts[u]["outputs"].shape[1] for u in order]
+            nseg, R = len(order), int(sum(widths))
+            seg_start = np.concatenate([[0], np.cumsum(widths)]).astype(np.int32)
+            row_seg = np.repeat(np.arange(nseg, dtype=np.int32), widths)
+            row_utt = np.repeat(np.asarray(order, dtype=np.int32), widths)
+            meta = i32(np.concatenate([seg_start, row_seg, row_utt, enc_len[order]]))
+            d_seg, d_rseg, d_rutt, d_len = (meta[:nseg + 1], meta[nseg + 1:nseg + 1 + R], meta[nseg + 1 + R:nseg + 1 + 2 * R],
+                                            meta[nseg + 1 + 2 * R:])
+            cost_so_far = torch.as_tensor(np.concatenate([utts[u]["costs"][-1] for u in order]).astype(np.float32), device=dev)
+            wavg = torch.empty((R, r.dim_encoded), dtype=torch.float32, device=dev)
+            new_w = torch.empty((R, Tp), dtype=torch.float32, device=dev)
+            new_e = torch.empty((R, Tp), dtype=torch.float32, device=dev)
+            top = torch.empty((3 * nseg * k + nseg,), dtype=torch.int32, device=dev)     # parent | symbol | cost bits | count
+            tp, ts, tcst, tcnt = top[:nseg * k], top[nseg * k:2 * nseg * k], top[2 * nseg * k:3 * nseg * k], top[3 * nseg * k:]
+            states, weights, step = states.contiguous(), weights.contiguous(), step.contiguous()
+            _lib.check(lib.lvsr_search_expand(
+                h, att.data_ptr(), P.data_ptr(), attm.data_ptr(), Tp, U, d_len.data_ptr(), d_rutt.data_ptr(), d_rseg.data_ptr(),
+                d_seg.data_ptr(), nseg, R, states.data_ptr(), weights.data_ptr(), step.data_ptr(), cost_so_far.data_ptr(), k,
+                wavg.data_ptr(), new_w.data_ptr(), new_e.data_ptr(), tp.data_ptr(), ts.data_ptr(), tcst.data_ptr(),
+                tcnt.data_ptr(), r._stream()))
+            top_h = top.cpu().numpy()                                   # the step's only device -> host transfer
+            parents_all = top_h[:nseg * k].reshape(nseg, k)
+            symbols_all = top_h[nseg * k:2 * nseg * k].reshape(nseg, k)
+            costs_all = top_h[2 * nseg * k:3 * nseg * k].view(np.float32).reshape(nseg, k)
+            counts = top_h[3 * nseg * k:]
+            # ---- the reference's bookkeeping per utterance (B/search.py:341-377) ----
+            sel_parent, sel_symbol, sel_widths, keep_after = [], [], [], []
+            base = 0
+            for sg, u in enumerate(order):
+                ut = utts[u]
+                cnt = int(counts[sg])
+                assert cnt >= 0, "non-finite log-probabilities"          # :340 assert numpy.isfinite(logprobs).all()
+                parents = parents_all[sg, :cnt].astype(np.int64) - int(seg_start[sg])
+                symbols = symbols_all[sg, :cnt].astype(np.int64)
+                chosen = costs_all[sg, :cnt]
+                ut["outputs"] = np.vstack([np.take(ut["outputs"], parents, axis=1), symbols[None, :]])
+                ut["costs"] = np.vstack([np.take(ut["costs"], parents, axis=1), chosen[None, :].astype(np.float32)])
+                alive = symbols != eol_symbol
+                if ignore_first_eol and i == 0:
+                    alive[:] = True
+                ended = np.where((ut["outputs"][-1] == eol_symbol) &
+                                 (ut["costs"][-1] - ut["costs"][-2] < round_to_inf))[0]
+                for idx in ended:
+                    iv = input_values[u] if input_values is not None else {"recordings": recordings_list[u][:, None, :]}
+                    if validate_solution_function is None or validate_solution_function(iv, ut["outputs"][:, idx]):
+                        ut["done"].append((ut["outputs"][:, idx], ut["costs"][:, idx]))
+                keep = np.where(alive)[0]
+                sel_parent.append(parents_all[sg, :cnt])
+                sel_symbol.append(symbols)
+                sel_widths.append(cnt)
+                keep_after.extend((base + keep).tolist())
+                base += cnt
+                ut["outputs"] = np.take(ut["outputs"], keep, axis=1)
+                ut["costs"] = np.take(ut["costs"], keep, axis=1)
+            # ---- next states of every selected child, then drop the finished ones ----
+            Rs = int(sum(sel_widths))
+            seg2 = np.concatenate([[0], np.cumsum(sel_widths)]).astype(np.int32)
+            meta2 = i32(np.concatenate([np.concatenate(sel_parent), seg2, np.repeat(np.arange(nseg, dtype=np.int32), sel_widths),
+                                        np.repeat(np.asarray(order, dtype=np.int32), sel_widths)]))
+            d_par, d_seg2, d_rseg2, d_rutt2 = meta2[:Rs], meta2[Rs:Rs + nseg + 1], meta2[Rs + nseg + 1:2 * Rs + nseg + 1], meta2[2 * Rs + nseg + 1:]
+            d_sym = torch.as_tensor(np.concatenate(sel_symbol).astype(np.int64), device=dev)
+            n_states = torch.empty((Rs, states.shape[1]), dtype=torch.float32, device=dev)
+            n_wavg = torch.empty((Rs, r.dim_encoded), dtype=torch.float32, device=dev)
+            n_w = torch.empty((Rs, Tp), dtype=torch.float32, device=dev)
+            n_e = torch.empty((Rs, Tp), dtype=torch.float32, device=dev)
+            n_step = torch.empty((Rs,), dtype=torch.int64, device=dev)
+            _lib.check(lib.lvsr_search_advance(
+                h, att.data_ptr(), P.data_ptr(), attm.data_ptr(), Tp, U, d_len.data_ptr(), Rs, d_par.data_ptr(), d_sym.data_ptr(),
+                d_rutt2.data_ptr(), d_rseg2.data_ptr(), d_seg2.data_ptr(), nseg, states.data_ptr(), weights.data_ptr(),
+                step.data_ptr(), wavg.data_ptr(), new_w.data_ptr(), new_e.data_ptr(), reuse, n_states.data_ptr(),
+                n_wavg.data_ptr(), n_w.data_ptr(), n_e.data_ptr(), n_step.data_ptr(), r._stream()))
+            if len(keep_after) != Rs:
+                sel = torch.as_tensor(np.asarray(keep_after, dtype=np.int64), device=dev)
+                states, weights, step = n_states.index_select(0, sel), n_w.index_select(0, sel), n_step.index_select(0, sel)
             else:
-                raise ValueError("Unknown stopping criterion {}".format(stop_on))
+                states, weights, step = n_states, n_w, n_step
 
-            logprobs = self.compute_logprobs(contexts, states).cpu().numpy()
-            assert np.isfinite(logprobs).all()
-            next_costs = costs_hist[-1, :, None] + logprobs
-            (parents, symbols), chosen = self._smallest(next_costs, self.beam_size)
-
-            sel = torch.as_tensor(parents, device=states["states"].device)
-            states = {k: v.index_select(0, sel) for k, v in states.items()}
-            outputs_hist = np.take(outputs_hist, parents, axis=1)
-            costs_hist = np.take(costs_hist, parents, axis=1)
-
-            states = self.compute_next_states(contexts, states, symbols)
-            outputs_hist = np.vstack([outputs_hist, symbols[None, :]])
-            costs_hist = np.vstack([costs_hist, chosen[None, :].astype(costs_hist.dtype)])
-
-            alive = symbols != eol_symbol
-            if ignore_first_eol and i == 0:
-                alive[:] = True
-            ended = np.where((outputs_hist[-1] == eol_symbol) &
-                             (costs_hist[-1] - costs_hist[-2] < round_to_inf))[0]
-            for idx in ended:
-                if (validate_solution_function is None or
-                        validate_solution_function(input_values, outputs_hist[:, idx])):
-                    done.append((outputs_hist[:, idx], costs_hist[:, idx]))
-            keep = np.where(alive)[0]
-            sel = torch.as_tensor(keep, device=states["states"].device)
-            states = {k: v.index_select(0, sel) for k, v in states.items()}
-            outputs_hist = np.take(outputs_hist, keep, axis=1)
-            costs_hist = np.take(costs_hist, keep, axis=1)
-
-        if not done:
-            raise CandidateNotFoundError()
-        done = sorted(done, key=discounted)
-
-        max_len = max(seq.shape[0] for seq, _ in done)
-        all_outputs = np.zeros((max_len, len(done)))
-        all_masks = np.zeros((max_len, len(done)))
-        all_costs = np.zeros((max_len, len(done)))
-        for j, (seq, cost) in enumerate(done):
-            all_outputs[:len(seq), j] = seq
-            all_masks[:len(seq), j] = 1
-            all_costs[:len(cost), j] = cost
-            all_costs[len(cost):, j] = cost[-1]
-        result = (all_outputs[1:], all_masks[1:], all_costs[1:] - all_costs[:-1])
-        if as_arrays:
-            return result
-        return self.result_to_lists(result)
+        results = []
+        for u in range(U):
+            done = utts[u]["done"]
+            if not done:
+                if raise_on_failure:
+                    raise CandidateNotFoundError()
+                results.append(None)
+                continue
+            done = sorted(done, key=discounted)
+            max_len = max(seq.shape[0] for seq, _ in done)
+            all_outputs = np.zeros((max_len, len(done)))
+            all_masks = np.zeros((max_len, len(done)))
+            all_costs = np.zeros((max_len, len(done)))
+            for j, (seq, cost) in enumerate(done):
+                all_outputs[:len(seq), j] = seq
+                all_masks[:len(seq), j] = 1
+                all_costs[:len(cost), j] = cost
+                all_costs[len(cost):, j] = cost[-1]
+            result = (all_outputs[1:], all_masks[1:], all_costs[1:] - all_costs[:-1])
+            results.append(result if as_arrays else self.result_to_lists(result))
+        return results
 
     @staticmethod
     def result_to_lists(result):

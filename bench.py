@@ -247,7 +247,7 @@ def train_bench(pkg, torch, dev, rank, world, steps, warmup, dist_mod, flush, ba
     lib.lvsr_profile_enable(1)
     algo.process_batch(dbatch)
     torch.cuda.synchronize(dev)
-    for cls in ("gemm", "gemm_tn", "bigru", "bigru_bwd", "dec_scan", "dec_bwd_step", "readout"):
+    for cls in ("gemm", "gemm_tn", "bigru", "bigru_bwd", "dec_scan", "dec_bwd_step", "att_bwd", "skinny", "window", "readout"):
         tot, cnt = C.c_double(), C.c_int64()
         lib.lvsr_profile_read(cls.encode(), C.byref(tot), C.byref(cnt))
         prof[cls] = {"ms": round(tot.value, 3), "launches": cnt.value}

@@ -135,6 +135,38 @@ int lvsr_next_states(lvsr_model* m, const float* attended_dev, const float* prep
                      float* next_weights_dev, float* next_energies_dev, int64_t* next_step_dev,
                      void* stream);
 
+/* ---- batched beam search: one step for MANY utterances --------------------------------------------
+ * The hypotheses (rows) of utterance s are the contiguous rows [seg_start[s], seg_start[s+1]) -- one segment is
+ * what the reference calls the batch inside BeamSearch.search (libs/blocks/blocks/search.py:244-399), so the
+ * batch-global window cut of take_glimpses is taken per segment.  row_utt[r] = column of the row's utterance in
+ * attended / preprocessed / attended_mask [T',U,.]; row_seg[r] = its segment; utt_len[s] = valid encoded frames of
+ * the segment's utterance (NULL: T').  All hypothesis state stays on the device:
+ *
+ *   lvsr_search_expand  = logprobs_computer + BeamSearch._smallest (:109-117,220-242,341-344): take_glimpses once per
+ *     row (kept in wavg / new_weights / new_energies for lvsr_search_advance), readout, -log softmax, and per
+ *     segment the k smallest cost_so_far + (-logp) in increasing order: top_parent (row index), top_symbol,
+ *     top_cost [nseg * k], top_count [nseg] (= min(k, width * V); -1 if a log-probability was not finite).
+ *     Only these k triples per utterance have to reach the host.
+ *   lvsr_search_advance = next_state_computer (:119-142) for the Rn selected children (parent rows + symbols):
+ *     gathers the parents' state and -- reuse_glimpses != 0 -- their glimpses (exact when the window does not
+ *     depend on which rows are in the batch: the expanding prior), else recomputes take_glimpses over the selected
+ *     rows as the reference does (window_around_* priors); then Distribute + GRU step; step + 1. */
+int lvsr_search_expand(lvsr_model* m, const float* attended_dev, const float* preprocessed_dev,
+                       const float* attended_mask_dev, int32_t Tp, int32_t U, const int32_t* utt_len_dev,
+                       const int32_t* row_utt_dev, const int32_t* row_seg_dev, const int32_t* seg_start_dev,
+                       int32_t nseg, int32_t R, const float* states_dev, const float* weights_dev,
+                       const int64_t* step_dev, const float* cost_so_far_dev, int32_t k, float* wavg_dev,
+                       float* new_weights_dev, float* new_energies_dev, int32_t* top_parent_dev,
+                       int32_t* top_symbol_dev, float* top_cost_dev, int32_t* top_count_dev, void* stream);
+int lvsr_search_advance(lvsr_model* m, const float* attended_dev, const float* preprocessed_dev,
+                        const float* attended_mask_dev, int32_t Tp, int32_t U, const int32_t* utt_len_dev, int32_t Rn,
+                        const int32_t* parent_dev, const int64_t* symbols_dev, const int32_t* row_utt_dev,
+                        const int32_t* row_seg_dev, const int32_t* seg_start_dev, int32_t nseg, const float* states_dev,
+                        const float* weights_dev, const int64_t* step_dev, const float* wavg_dev,
+                        const float* new_weights_dev, const float* new_energies_dev, int32_t reuse_glimpses,
+                        float* next_states_dev, float* next_wavg_dev, float* next_weights_dev,
+                        float* next_energies_dev, int64_t* next_step_dev, void* stream);
+
 /* ---- host-buffer entry points (the call a user of the reference makes) -------------
  * SpeechRecognizer.cost on a batch (lvsr/bricks/recognizer.py:375-390): H2D copies,
  * encoder, cost_matrix, D2H of costs [L,B]; synchronises.  Buffers should be pinned. */
