@@ -15,6 +15,7 @@ No symbolic graph exists: every method is a direct call into liblvsr_b200.so (C 
 include/lvsr_b200.h) on torch-owned device buffers.  There is no CPU fallback.
 """
 import io
+import logging
 import tarfile
 from collections import OrderedDict
 
@@ -23,6 +24,20 @@ import numpy as np
 from . import _lib
 from . import bricks as _bricks
 from .search import BeamSearch, CandidateNotFoundError  # noqa: F401
+
+
+logger = logging.getLogger(__name__)
+
+
+class _Variable(object):
+    """Stand-in for the Theano input variables lvsr/main.py reads the NAMES of (recognizer.inputs.keys(),
+    recognizer.labels.name ...: lvsr/bricks/recognizer.py:351-361, lvsr/main.py:260-262,786)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return self.name
 
 
 def _ptr(t):
@@ -119,10 +134,20 @@ class SpeechRecognizer(object):
         self.bottom = _Child("bottom")
         self.children = [self.encoder, self.top, self.bottom, self.generator]
 
+        # named inputs of the reference's graphs (lvsr/bricks/recognizer.py:351-361)
+        self.inputs = OrderedDict(recordings=_Variable("recordings"))
+        self.single_inputs = OrderedDict(recordings=_Variable("recordings"))
+        self.inputs_mask = _Variable("recordings_mask")
+        self.labels = _Variable("labels")
+        self.labels_mask = _Variable("labels_mask")
+        self.single_labels = _Variable("labels")
+        self.n_steps = _Variable("n_steps")
+
         self._device = device
         self._handle = None
         self._beam_search = None
         self.beam_size = None
+        self._ctor_state = None
 
     # ------------------------------------------------------------------------------
     # handle / device
@@ -257,7 +282,9 @@ class SpeechRecognizer(object):
 
     def load_params(self, path):
         """Blocks checkpoint (tar with a ``_parameters`` npz whose keys use '|' for '/':
-        libs/blocks/blocks/serialization.py:264-282,606-610) or a plain .npz."""
+        libs/blocks/blocks/serialization.py:264-282,606-610) or a plain .npz.  Like
+        Model.set_parameter_values (libs/blocks/blocks/model.py:120-146) unknown names and missing parameters
+        are LOGGED, not raised; missing parameters keep their current values."""
         data = None
         if tarfile.is_tarfile(path):
             with tarfile.open(path) as tar:
@@ -265,10 +292,48 @@ class SpeechRecognizer(object):
         else:
             data = np.load(path)
         values = {k.replace("|", "/"): data[k] for k in data.files}
-        self.set_parameter_values({k: v for k, v in values.items() if k.startswith("/recognizer")})
+        shapes = self.parameter_shapes()
+        unknown = sorted(set(values) - set(shapes))
+        missing = sorted(set(shapes) - set(values))
+        if unknown:
+            logger.error("unknown parameter names: {}\n".format(unknown))
+        if missing:
+            logger.error("missing values for parameters: {}\n".format(missing))
+        self.set_parameter_values({k: v for k, v in values.items() if k in shapes})
+        return dict(unknown=unknown, missing=missing)
 
     def save_params(self, path):
-        np.savez(path, **{k.replace("/", "|"): v for k, v in self.get_parameter_values().items()})
+        """Write the parameters the way blocks.serialization.dump stores them separately: a tar archive with one
+        member ``_parameters`` = numpy.savez of {brick path with '|' for '/': array}
+        (libs/blocks/blocks/serialization.py:136,264-282,493-500,606-610) -- readable by the reference's
+        load_parameters and by load_params above."""
+        buf = io.BytesIO()
+        np.savez(buf, **{k.replace("/", "|"): v for k, v in self.get_parameter_values().items()})
+        payload = buf.getvalue()
+        with tarfile.open(path, "w") as tar:
+            info = tarfile.TarInfo("_parameters")
+            info.size = len(payload)
+            tar.addfile(info, io.BytesIO(payload))
+
+    # pickling: device handles do not travel (lvsr/bricks/recognizer.py:549-562 drops the compiled functions)
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for attr in ("_handle", "_beam_search", "_generator_state"):
+            state.pop(attr, None)
+        state["_device"] = None if self._device is None else str(self._device)
+        state["_saved_parameters"] = None if self._handle is None else self.get_parameter_values()
+        return state
+
+    def __setstate__(self, state):
+        saved = state.pop("_saved_parameters", None)
+        self.__dict__.update(state)
+        self._handle = None
+        self._beam_search = None
+        if saved is not None:
+            try:
+                self.set_parameter_values(saved)
+            except RuntimeError:           # unpickled where no GPU is visible: parameters stay on the host copy
+                self._pending_parameters = saved
 
     # ------------------------------------------------------------------------------
     # device-side operators (torch tensors in, torch tensors out)
@@ -450,6 +515,60 @@ class SpeechRecognizer(object):
         max_lengths = [int(x.shape[0] / self.max_decoded_length_scale) for x in recs]
         return self._beam_search.search_many(recs, self.eos_label, max_lengths,
                                              ignore_first_eol=self.data_prepend_eos, **kwargs)
+
+    # ---- generate / sample (B/bricks/sequence_generators.py:328-377; recognizer.py:535-547) ----
+    def generate(self, recordings, recordings_mask=None, n_steps=None, sample=True, seed=None):
+        """SequenceGenerator.generate iterated n_steps times for a batch [T,B,F]: glimpses -> readout -> emit ->
+        feedback -> next state.  ``sample=True`` emits from the softmax like SoftmaxEmitter.emit
+        (sequence_generators.py:772-778; a seeded Philox stream on the device instead of Theano's MRG stream, so
+        draws differ from the reference while their distribution does not), ``sample=False`` emits the arg-max.
+        Returns dict(outputs [n,B] int64, costs [n,B] = -log p(emitted), states [n,B,C], weights [n,B,T'])."""
+        torch = self._torch()
+        att, attm = self.encode(recordings, recordings_mask)
+        B, Tp = att.shape[1], att.shape[0]
+        if n_steps is None:
+            n_steps = int(np.asarray(recordings).shape[0] / self.max_decoded_length_scale)
+        ctx = dict(attended=att, attended_mask=attm, preprocessed=self.preprocess(att))
+        st = self._initial_states(Tp, B)
+        gen = None
+        if sample:
+            gen = torch.Generator(device=self.device)
+            gen.manual_seed(1 if seed is None else int(seed))
+        outs, costs, states, weights = [], [], [], []
+        for _ in range(int(n_steps)):
+            neglogp = self._logprobs(ctx, st)
+            if sample:
+                y = torch.multinomial(torch.exp(-neglogp), 1, generator=gen)[:, 0]
+            else:
+                y = neglogp.argmin(dim=1)
+            costs.append(neglogp.gather(1, y[:, None])[:, 0])
+            st = self._next_states(ctx, st, y)
+            outs.append(y)
+            states.append(st["states"])
+            weights.append(st["weights"])
+        return dict(outputs=torch.stack(outs).cpu().numpy(), costs=torch.stack(costs).cpu().numpy(),
+                    states=torch.stack(states).cpu().numpy(), weights=torch.stack(weights).cpu().numpy())
+
+    def sample(self, inputs, n_steps=None, seed=None):
+        """recognizer.py:540-547: one utterance {'recordings': [T,F]} -> sampled outputs [n_steps, 1]."""
+        rec = np.asarray(dict(inputs)["recordings"], dtype=np.float32)[:, None, :]
+        if n_steps is None:
+            n_steps = int(rec.shape[0] / self.max_decoded_length_scale)
+        return self.generate(rec, None, n_steps=n_steps, sample=True, seed=seed)["outputs"]
+
+    def get_generate_graph(self, use_mask=True, n_steps=None):
+        """recognizer.py:414-421 returns the symbolic generate application; here: a callable with the same inputs
+        (recordings [, recordings_mask], n_steps) returning the dict of generate()."""
+        def run(recordings, recordings_mask=None, n_steps=n_steps, **kw):
+            return self.generate(recordings, recordings_mask if use_mask else None, n_steps=n_steps, **kw)
+        return run
+
+    def get_cost_graph(self, batch=True, prediction=None, prediction_mask=None):
+        """recognizer.py:423-450: the cost 'graph' as a callable: batch=True takes (recordings, recordings_mask, labels,
+        labels_mask) -> costs [L,B]; batch=False takes one utterance (recordings [T,F], labels [L]) -> costs [L]."""
+        if batch:
+            return lambda recordings, recordings_mask, labels, labels_mask: self.cost(recordings, recordings_mask, labels, labels_mask)
+        return lambda recordings, labels: self.analyze({"recordings": recordings}, labels)[0]
 
     # ------------------------------------------------------------------------------
     # BeamSearch state functions (C-ABI calls)

@@ -270,6 +270,181 @@ def train_bench(pkg, torch, dev, rank, world, steps, warmup, dist_mod, flush, ba
     }
 
 
+SEARCH_CASES = {
+    # BASELINE.json configs[0]: 8 utterances x 200 frames, 1-layer BiGRU(128), greedy decode
+    "config1_greedy": dict(U=8, T=200, beam=1, scale=8.0,
+                           net=dict(num_features=40, dims_bidir=[128], subsample=[1], dim_dec=128, conv_n=100,
+                                    conv_num_filters=10, num_phonemes=32, post_merge_dims=[128], maxout_pieces=2)),
+    # configs[2]: WSJ-shaped, 32 utterances x 800 frames, beam_size = 10, char-level output
+    "config3_beam10": dict(U=32, T=800, beam=10, scale=8.0, net=NET),
+}
+SEARCH_METRIC = "beam-search utterances/sec at 32x800frx40fb, WSJ architecture, beam_size=10 (configs[2])"
+
+
+def search_values(shapes, seed=1):
+    """'Trained-like' weights (init_values) with a sharper readout so that hypotheses of many lengths finish."""
+    v = init_values(shapes, seed=seed)
+    v["/recognizer/generator/readout/post_merge/mlp/linear_0.W"] *= 10.0
+    v["/recognizer/generator/readout/post_merge/mlp/linear_0.b"][-1] = 1.0        # eos = V - 1
+    return v
+
+
+def search_bench(pkg, torch, dev, rank, world, steps, warmup, dist_mod, barrier, cpu_baseline=True):
+    """Decode U utterances per GPU with BeamSearch.search_many (device-resident hypotheses, k-best on the GPU);
+    wall clock around the call (recordings start in HOST memory: the encoder H2D copy is inside), max over ranks."""
+    out = {}
+    lib = pkg._lib.load()
+    for name, case in SEARCH_CASES.items():
+        net = case["net"]
+        rec = pkg.SpeechRecognizer(
+            input_dims={"recordings": 40}, input_num_chars={}, eos_label=31, num_phonemes=32, dim_dec=net["dim_dec"],
+            dims_bidir=net["dims_bidir"], subsample=net["subsample"], conv_n=net["conv_n"],
+            conv_num_filters=net["conv_num_filters"], dim_matcher=net.get("dim_matcher"),
+            post_merge_dims=net["post_merge_dims"], post_merge_activation=pkg.Maxout(2),
+            max_decoded_length_scale=case["scale"], data_prepend_eos=False,
+            enc_transition=pkg.GatedRecurrent, dec_transition=pkg.GatedRecurrent, device=dev)
+        values = search_values(rec.parameter_shapes())
+        rec.set_parameter_values(values)
+        rec.init_beam_search(case["beam"])
+        rng = np.random.RandomState(99 + rank)
+        lens = rng.randint(int(0.6 * case["T"]), case["T"] + 1, size=case["U"])
+        lens[0] = case["T"]
+        utts = [rng.normal(size=(int(t), 40)).astype(np.float32) for t in lens]
+        inputs = [{"recordings": u} for u in utts]
+        res = None
+        for _ in range(max(1, warmup)):
+            res = rec.beam_search_many(inputs, raise_on_failure=False)
+        barrier()
+        lib.lvsr_launch_count(1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = rec.beam_search_many(inputs, raise_on_failure=False)
+        torch.cuda.synchronize(dev)
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev, dist_mod) / steps
+        launches = int(lib.lvsr_launch_count(1)) // max(1, steps)
+        found = [r for r in res if r is not None]
+        tok = [len(r[0][0]) for r in found]
+        entry = {"utterances_per_s": case["U"] * world / (ms * 1e-3), "frames_per_s": float(lens.sum()) * world / (ms * 1e-3),
+                 "ms_per_batch": ms, "utterances_per_gpu": case["U"], "beam_size": case["beam"], "max_frames": case["T"],
+                 "decoded": len(found), "mean_best_length": float(np.mean(tok)) if tok else 0.0,
+                 "gpu_launches_per_batch": launches}
+        if cpu_baseline and rank == 0:
+            from oracle import lvsr_oracle as O
+            cfg = O.make_config(max_decoded_length_scale=case["scale"], **net)
+            p32 = {k: v.astype(np.float32) for k, v in values.items()}
+            n = 1 if case["beam"] > 1 else 2
+            t0 = time.perf_counter()
+            same = 0
+            for u, r in list(zip(utts, res))[:n]:
+                try:
+                    o = O.beam_search(cfg, p32, u, case["beam"])
+                    same += int(r is not None and o[0][0] == r[0][0])
+                except O.CandidateNotFoundError:
+                    same += int(r is None)
+            dt = time.perf_counter() - t0
+            entry["cpu_oracle_utterances_per_s"] = n / dt
+            entry["cpu_oracle_sample"] = "%d utterance(s), float32 numpy restatement of BeamSearch.search" % n
+            entry["best_hypothesis_identical_to_cpu_oracle"] = "%d/%d" % (same, n)
+        out[name] = entry
+        del rec
+    return out
+
+
+STRESS_NET = dict(num_features=40, dims_bidir=[256, 256, 256], subsample=[1, 1, 1], dim_dec=256, dim_matcher=512, conv_n=100,
+                  conv_num_filters=10, num_phonemes=63, post_merge_dims=[256], maxout_pieces=2)
+STRESS_WORKLOAD = dict(B=16, T=2000, F=40, L=60, V=63)       # BASELINE.json configs[4]: 128 utterances over 8 GPUs
+STRESS_METRIC = "encoder+decoder frames/sec, TIMIT-shaped long utterances: batch 128 x 2000fr x 40fb over 8 GPUs (configs[4])"
+
+
+def stress_bench(pkg, torch, dev, rank, world, steps, warmup, dist_mod, flush, barrier):
+    """configs[4]: 16 utterances x 2000 frames per GPU, 3 x BiGRU(256) without subsampling (T' = 2000), 63 symbols,
+    window_around_median(100, 100): teacher-forced cost; HBM GB/s of the decoder kernel and the tensor-core rate of the
+    fork GEMMs against the measured peaks."""
+    import ctypes as C
+    W = STRESS_WORKLOAD
+    rec = pkg.SpeechRecognizer(
+        input_dims={"recordings": W["F"]}, input_num_chars={}, eos_label=W["V"] - 1, num_phonemes=W["V"],
+        dim_dec=STRESS_NET["dim_dec"], dims_bidir=STRESS_NET["dims_bidir"], subsample=STRESS_NET["subsample"],
+        conv_n=STRESS_NET["conv_n"], conv_num_filters=STRESS_NET["conv_num_filters"], dim_matcher=STRESS_NET["dim_matcher"],
+        post_merge_dims=STRESS_NET["post_merge_dims"], post_merge_activation=pkg.Maxout(2),
+        prior=dict(type="window_around_median", before=100, after=100),
+        enc_transition=pkg.GatedRecurrent, dec_transition=pkg.GatedRecurrent, device=dev)
+    rec.set_parameter_values(init_values(rec.parameter_shapes()))
+    lib = pkg._lib.load()
+    x, m, labels, lm = synthetic_batch(W["B"], W["T"], W["F"], W["L"], W["V"], seed=shard_seed(rank, base=777))
+    xd, md = torch.as_tensor(x, device=dev), torch.as_tensor(m, device=dev)
+    yd, ymd = torch.as_tensor(labels, device=dev), torch.as_tensor(lm, device=dev)
+
+    def step():
+        att, attm = rec.encode(xd, md)
+        return rec.cost_matrix(yd, ymd, att, attm, return_all=True)
+    for _ in range(max(3, warmup)):
+        r = step()
+    barrier()
+    total = 0.0
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        total += a.elapsed_time(b)
+    ms = max_over_ranks(total, world, dev, dist_mod) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rec.cost(x, m, labels, lm)
+    ms_host = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev, dist_mod) / steps
+    prof = {}
+    lib.lvsr_profile_enable(1)
+    r = step()
+    torch.cuda.synchronize(dev)
+    for cls in ("gemm", "bigru", "dec_scan", "attention", "window", "dense", "readout"):
+        tot, cnt = C.c_double(), C.c_int64()
+        lib.lvsr_profile_read(cls.encode(), C.byref(tot), C.byref(cnt))
+        prof[cls] = {"ms": round(tot.value, 3), "launches": cnt.value}
+    lib.lvsr_profile_enable(0)
+    # the window actually attended: positions with non-zero alignment or inside the cut -> algorithmic bytes of the decoder
+    w = r["weights"]                                  # [L, B, T']
+    Tp = w.shape[2]
+    nz = (w > 0).any(dim=1)                           # [L, T'] union over the batch = the batch-global cut, at least
+    first = torch.where(nz.any(dim=1), nz.float().argmax(dim=1), torch.zeros_like(nz[:, 0], dtype=torch.long))
+    last = torch.where(nz.any(dim=1), Tp - 1 - nz.flip(1).float().argmax(dim=1), torch.zeros_like(first))
+    tw = (last - first + 1).float().mean().item()
+    peaks, peak_src = measured_peaks()
+    M, E = STRESS_NET["dim_matcher"], 2 * STRESS_NET["dims_bidir"][-1]
+    persistent = prof["attention"]["launches"] == 0          # the class is recorded even when the planner declines the shape
+    dec_ms = prof["dec_scan"]["ms"] if persistent else (prof["attention"]["ms"] + prof["dense"]["ms"] + prof["window"]["ms"])
+    step_bytes = attention_step_bytes(W["B"], tw, M, E)
+    hbm = step_bytes * W["L"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+    gemm_flops, t_l, din = 0.0, W["T"], W["F"]
+    for D in STRESS_NET["dims_bidir"]:
+        gemm_flops += 2.0 * t_l * W["B"] * din * 6 * D
+        din = 2 * D
+    gemm_flops += 2.0 * Tp * W["B"] * E * M
+    tf = gemm_flops / (prof["gemm"]["ms"] * 1e-3) / 1e12 if prof["gemm"]["ms"] > 0 else 0.0
+    frames = W["B"] * W["T"] * world
+    return {
+        "metric": STRESS_METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "n_gpus": world,
+        "steps": steps, "scaling": "weak", "dtype": "f32",
+        "config": {"workload": "configs[4]: %d utterances x %d frames x %d fbank per GPU, 3 x BiGRU(256), no subsampling (T' = %d), "
+                               "%d symbols, window_around_median(100,100), %d teacher-forced steps" % (W["B"], W["T"], W["F"], Tp, W["V"], W["L"]),
+                   "global_batch": W["B"] * world, "parallelism": "dp%d (utterance shards, no data-path collective)" % world},
+        "e2e": {"value": frames / (ms_host * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": int(x.nbytes + m.nbytes + labels.nbytes + lm.nbytes), "d2h_bytes_per_step": int(W["L"] * W["B"] * 4)},
+        "decoder": {"path": "persistent dec_scan_kernel" if persistent else
+                            "step-wise kernels (window / att_step / dense): 16 rows x T' = 2000 needs 16 co-resident 8-CTA clusters "
+                            "or 500-position chunks, neither fits (dec_scan.cu planner)",
+                    "mean_window_positions": tw, "algorithmic_bytes_per_step": step_bytes, "us_per_step": dec_ms * 1e3 / W["L"],
+                    "hbm_GBps": hbm, "hbm_frac_of_measured_peak": hbm / peaks["hbm_gbs"], "peak_source": peak_src},
+        "fork_gemms": {"useful_tflops": tf, "tensor_pipe_frac_3xtf32": 3.0 * tf / (peaks["bf16_tflops"] / 2.0),
+                       "note": "3 tf32 products per useful product (exact hi/lo split); tf32 dense peak taken as half the measured bf16 peak; "
+                               "layer 0 (K = 40) runs on FFMA tiles and is included in the time"},
+        "kernel_ms_per_step": prof,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,7 +452,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="metric", choices=["metric", "train"],
+    ap.add_argument("--mode", default="metric", choices=["metric", "train", "search", "stress"],
                     help="metric: the BASELINE headline (forward cost, teacher forcing) with a `train` block for the "
                          "training step; train: the training step (configs[3]) as the main line")
     ap.add_argument("--no-train", action="store_true", help="metric mode: skip the training-step block")
@@ -365,6 +540,34 @@ def main():
     dist_mod = None
     if world > 1:
         import torch.distributed as dist_mod
+
+    if args.mode in ("search", "stress"):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        if args.mode == "search":
+            sr = search_bench(pkg, torch, dev, rank, world, max(1, min(args.steps, 3)), 1, dist_mod, barrier,
+                              cpu_baseline=not args.no_cpu_baseline)
+            main_case = sr["config3_beam10"]
+            line = {"metric": SEARCH_METRIC, "value": main_case["utterances_per_s"], "unit": "utterances/s", "n_gpus": world,
+                    "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": main_case["ms_per_batch"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": "configs[2]: 32 utterances x <=800 frames per GPU, beam_size 10; configs[0] in `search`",
+                               "parallelism": "dp%d (utterances sharded, no cross-device traffic)" % world},
+                    "e2e": {"value": main_case["utterances_per_s"], "unit": "utterances/s",
+                            "h2d_bytes_per_step": int(main_case["frames_per_s"] * main_case["ms_per_batch"] * 1e-3 / world * 40 * 4),
+                            "d2h_bytes_per_step": 0, "note": "recordings start in host memory; value == e2e for this mode"},
+                    "gpu_launches": main_case["gpu_launches_per_batch"], "search": sr}
+        else:
+            line = stress_bench(pkg, torch, dev, rank, world, args.steps, args.warmup, dist_mod, flush, barrier)
+            line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+        if rank == 0:
+            line["clocks"] = sampler.summary()
+            print(json.dumps(line))
+        if world > 1:
+            dist_mod.destroy_process_group()
+        return 0
 
     if args.mode == "train":
         sampler = ClockSampler(local_rank)
