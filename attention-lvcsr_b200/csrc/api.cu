@@ -208,7 +208,7 @@ size_t encoder_ws_bytes(const lvsr_model* m, int T, int B) {
     const int D = m->cfg.dims_bidir[l], k = m->cfg.subsample[l];
     const int Tout = ceil_div(Tl, k);
     total += ((size_t)Tl * B * 6 * D + (size_t)Tout * B * 2 * D) * sizeof(float) + 1024;
-    total += (size_t)2 * Tl * B * (l == 0 ? m->cfg.num_features : 2 * m->cfg.dims_bidir[l - 1]) * sizeof(float) + 1024;
+    total += (size_t)2 * Tl * B * gemm_tc_kpad(l == 0 ? m->cfg.num_features : 2 * m->cfg.dims_bidir[l - 1]) * sizeof(float) + 1024;
     Tl = Tout;
   }
   return total + (1 << 16);
@@ -457,16 +457,16 @@ int finalize_on_stream(lvsr_model* m, cudaStream_t st, bool synchronise) {
         const int D = c.dims_bidir[l];
         float *h = nullptr, *lo = nullptr;
         if (gemm_tc_supported(128, 6 * D, dk)) {
-          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h), (size_t)dk * 6 * D * sizeof(float)));
-          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&lo), (size_t)dk * 6 * D * sizeof(float)));
+          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h), (size_t)gemm_tc_kpad(dk) * 6 * D * sizeof(float)));
+          LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&lo), (size_t)gemm_tc_kpad(dk) * 6 * D * sizeof(float)));
         }
         m->Wcat_hi.push_back(h);
         m->Wcat_lo.push_back(lo);
         dk = 2 * D;
       }
       if (gemm_tc_supported(128, c.dim_matcher, m->E)) {
-        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_hi), (size_t)m->E * c.dim_matcher * sizeof(float)));
-        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_lo), (size_t)m->E * c.dim_matcher * sizeof(float)));
+        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_hi), (size_t)gemm_tc_kpad(m->E) * c.dim_matcher * sizeof(float)));
+        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_lo), (size_t)gemm_tc_kpad(m->E) * c.dim_matcher * sizeof(float)));
       }
     }
     int dk = c.num_features;
@@ -524,8 +524,8 @@ int lvsr_encoder_forward(lvsr_model* m, const float* x, const float* mask, int32
     LVSR_CHECK(pre, "out of device memory (encoder pre-activations)");
     if (m->use_tc && l < (int)m->Wcat_hi.size() && m->Wcat_hi[l] && gemm_tc_supported(rows, 6 * D, din)) {
       const size_t mark = m->ws.off;
-      float* a_hi = m->ws.f32((size_t)rows * din);
-      float* a_lo = m->ws.f32((size_t)rows * din);
+      float* a_hi = m->ws.f32((size_t)rows * gemm_tc_kpad(din));
+      float* a_lo = m->ws.f32((size_t)rows * gemm_tc_kpad(din));
       LVSR_CHECK(a_hi && a_lo, "out of device memory (tf32 split scratch)");
       if (int rc = gemm_tc(cur, a_hi, a_lo, rows, din, m->Wcat_hi[l], m->Wcat_lo[l], 6 * D, m->bcat[l], pre, 6 * D, st)) return rc;
       if (m->ws.off <= m->ws.cap) m->ws.off = mark;     // scratch is dead once the GEMM is enqueued (stream order)
@@ -560,8 +560,8 @@ int lvsr_preprocess(lvsr_model* m, const float* attended, int32_t Tp, int32_t U,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (m->use_tc && m->Wp_hi && gemm_tc_supported(Tp * U, m->cfg.dim_matcher, m->E)) {
     ArenaScope scope(m, st);
-    float* a_hi = m->ws.f32((size_t)Tp * U * m->E);
-    float* a_lo = m->ws.f32((size_t)Tp * U * m->E);
+    float* a_hi = m->ws.f32((size_t)Tp * U * gemm_tc_kpad(m->E));
+    float* a_lo = m->ws.f32((size_t)Tp * U * gemm_tc_kpad(m->E));
     LVSR_CHECK(a_hi && a_lo, "out of device memory (tf32 split scratch)");
     return gemm_tc(attended, a_hi, a_lo, Tp * U, m->E, m->Wp_hi, m->Wp_lo, m->cfg.dim_matcher,
                    m->P(std::string(ATT) + "/preprocess.b"), out, m->cfg.dim_matcher, st);

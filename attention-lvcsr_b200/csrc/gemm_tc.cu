@@ -95,6 +95,8 @@ struct TcGemmParams {
   float* C;
   const float* bias;
   int M, N, K, ldc;
+  int kb_per_split;            // K blocks handled by one blockIdx.z (split-K: partial products, summed by the caller)
+  long long c_split_stride;    // elements between the partial outputs of consecutive splits
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -110,7 +112,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
-  const int nkb = p.K / TC_BK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, p.K / TC_BK - kb0);
+  p.C += (long long)blockIdx.z * p.c_split_stride;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -141,10 +145,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t full = smem_addr(&bars[s]);
         bar_expect_tx(full, TC_STAGE_BYTES);
         const uint32_t base = smem_addr(tiles + (size_t)s * TC_STAGE_BYTES);
-        tma_load_2d(base + 0 * TC_TILE_BYTES, &map_a_hi, kb * TC_BK, m0, full);
-        tma_load_2d(base + 1 * TC_TILE_BYTES, &map_a_lo, kb * TC_BK, m0, full);
-        tma_load_2d(base + 2 * TC_TILE_BYTES, &map_b_hi, kb * TC_BK, n0, full);
-        tma_load_2d(base + 3 * TC_TILE_BYTES, &map_b_lo, kb * TC_BK, n0, full);
+        tma_load_2d(base + 0 * TC_TILE_BYTES, &map_a_hi, (kb0 + kb) * TC_BK, m0, full);
+        tma_load_2d(base + 1 * TC_TILE_BYTES, &map_a_lo, (kb0 + kb) * TC_BK, m0, full);
+        tma_load_2d(base + 2 * TC_TILE_BYTES, &map_b_hi, (kb0 + kb) * TC_BK, n0, full);
+        tma_load_2d(base + 3 * TC_TILE_BYTES, &map_b_lo, (kb0 + kb) * TC_BK, n0, full);
       }
     }
   } else if (warp == 1) {
@@ -233,24 +237,40 @@ __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restri
 
 // [K, N] row-major -> K-major [N, K] hi/lo pair (weights, once per finalize)
 __global__ void transpose_split_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo,
-                                       int K, int N) {
+                                       int K, int N, int Kpad, int ldw) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int k = k0 + i, n = n0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < K && n < N) ? W[(long long)k * N + n] : 0.f;
+    tile[i][threadIdx.x] = (k < K && n < N) ? W[(long long)k * ldw + n] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int n = n0 + i, k = k0 + threadIdx.x;
-    if (n < N && k < K) {
+    if (n < N && k < Kpad) {                      // k in [K, Kpad): zero padding of the contraction dimension
       const float a = tile[threadIdx.x][i];
       const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
       uint32_t t;
       asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(t) : "f"(a - ah));
-      hi[(long long)n * K + k] = ah;
-      lo[(long long)n * K + k] = __uint_as_float(t);
+      hi[(long long)n * Kpad + k] = ah;
+      lo[(long long)n * Kpad + k] = __uint_as_float(t);
     }
+  }
+}
+
+// split + zero-pad the contraction dimension in one pass: x [M, K] -> hi / lo [M, Kpad] (layer 0: K = 40 -> 64)
+__global__ void split_pad_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                      long long M, int K, int Kpad) {
+  const long long total = M * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Kpad;
+    const int k = (int)(i % Kpad);
+    const float a = k < K ? x[r * K + k] : 0.f;
+    const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(t) : "f"(a - ah));
+    hi[i] = ah;
+    lo[i] = __uint_as_float(t);
   }
 }
 
@@ -284,45 +304,94 @@ int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
 
 }  // namespace
 
+// the contraction dimension is zero-padded to a multiple of the 32-float TMA box (layer 0: K = 40 -> 64)
+int gemm_tc_kpad(int K) { return ceil_div(K, TC_BK) * TC_BK; }
+
 bool gemm_tc_supported(int M, int N, int K) {
-  return M >= 1 && N % TC_BN == 0 && K % TC_BK == 0 && K >= TC_BK;
+  return M >= 1 && N % TC_BN == 0 && K >= 4 && K % 4 == 0;
 }
 
+// Wt_hi / Wt_lo: [N, gemm_tc_kpad(K)]
 int split_weight_tf32(const float* W, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream) {
-  dim3 grid(ceil_div(N, 32), ceil_div(K, 32)), block(32, 8);
-  transpose_split_kernel<<<grid, block, 0, stream>>>(W, Wt_hi, Wt_lo, K, N);
+  const int Kpad = gemm_tc_kpad(K);
+  dim3 grid(ceil_div(N, 32), ceil_div(Kpad, 32)), block(32, 8);
+  transpose_split_kernel<<<grid, block, 0, stream>>>(W, Wt_hi, Wt_lo, K, N, Kpad, N);
   LVSR_LAUNCH_CHECK();
   return 0;
 }
 
-// C[M,N] = A[M,K] . W + bias with W given as the K-major hi/lo pair produced by split_weight_tf32.
-// A_hi / A_lo: caller-provided scratch of M*K floats each.
-int gemm_tc(const float* A, float* A_hi, float* A_lo, int M, int K, const float* Wt_hi, const float* Wt_lo, int N,
-            const float* bias, float* C, int ldc, cudaStream_t stream) {
-  ProfScope prof("gemm", stream);
-  LVSR_CHECK(gemm_tc_supported(M, N, K), "gemm_tc: unsupported shape M=%d N=%d K=%d", M, N, K);
-  if (int rc = get_encode()) return rc;
-  const long long n4 = (long long)M * K / 4;
-  split_tf32_kernel<<<(int)std::min<long long>(4096, (n4 + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(A), reinterpret_cast<float4*>(A_hi), reinterpret_cast<float4*>(A_lo), n4);
+// [K rows, N columns, leading dimension ldw] -> K-major hi/lo [N, gemm_tc_kpad(K)] (operands of the TN product)
+int transpose_split_tf32(const float* W, int K, int N, int ldw, float* hi, float* lo, cudaStream_t stream) {
+  const int Kpad = gemm_tc_kpad(K);
+  dim3 grid(ceil_div(N, 32), ceil_div(Kpad, 32)), block(32, 8);
+  LVSR_CHECK(grid.y <= 65535, "transpose_split: too many rows (%d)", K);
+  transpose_split_kernel<<<grid, block, 0, stream>>>(W, hi, lo, K, N, Kpad, ldw);
   LVSR_LAUNCH_CHECK();
+  return 0;
+}
+
+// element-wise exact split x = hi + lo (n % 4 == 0)
+int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream) {
+  const long long n4 = n / 4;
+  split_tf32_kernel<<<(int)std::min<long long>(4096, (n4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n4);
+  LVSR_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc_splits_launched(int Kpad, int splits) {
+  const int total_kb = Kpad / TC_BK;
+  splits = std::max(1, std::min(splits, total_kb));
+  return ceil_div(total_kb, ceil_div(total_kb, splits));
+}
+
+// C[M,N] (+ bias) = A . B^T with both operands K-major hi/lo pairs: A [M, Kpad], B [N, Kpad].  splits > 1: split-K, partial
+// result z goes to C + z * split_stride (the caller adds them up).
+int gemm_tc_presplit(const float* A_hi, const float* A_lo, int M, const float* B_hi, const float* B_lo, int N, int Kpad,
+                     const float* bias, float* C, int ldc, int splits, long long split_stride, cudaStream_t stream) {
+  ProfScope prof("gemm", stream);
+  LVSR_CHECK(M >= 1 && N % TC_BN == 0 && Kpad % TC_BK == 0 && Kpad >= TC_BK && splits >= 1, "gemm_tc_presplit: unsupported shape M=%d N=%d K=%d", M, N, Kpad);
+  if (int rc = get_encode()) return rc;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (int rc = make_map(&ma_hi, A_hi, M, K)) return rc;
-  if (int rc = make_map(&ma_lo, A_lo, M, K)) return rc;
-  if (int rc = make_map(&mb_hi, Wt_hi, N, K)) return rc;
-  if (int rc = make_map(&mb_lo, Wt_lo, N, K)) return rc;
+  if (int rc = make_map(&ma_hi, A_hi, M, Kpad)) return rc;
+  if (int rc = make_map(&ma_lo, A_lo, M, Kpad)) return rc;
+  if (int rc = make_map(&mb_hi, B_hi, N, Kpad)) return rc;
+  if (int rc = make_map(&mb_lo, B_lo, N, Kpad)) return rc;
   static bool configured[LVSR_MAX_DEVICES] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
     LVSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured[dev] = true;
   }
+  const int total_kb = Kpad / TC_BK;
+  splits = std::min(splits, total_kb);
   TcGemmParams p;
-  p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  dim3 grid(N / TC_BN, ceil_div(M, TC_BM));
+  p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = Kpad; p.ldc = ldc;
+  p.kb_per_split = ceil_div(total_kb, splits);
+  p.c_split_stride = split_stride;
+  dim3 grid(N / TC_BN, ceil_div(M, TC_BM), ceil_div(total_kb, p.kb_per_split));
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   LVSR_LAUNCH_CHECK();
   return 0;
+}
+
+// C[M,N] = A[M,K] . W + bias with W given as the K-major hi/lo pair produced by split_weight_tf32.
+// A_hi / A_lo: caller-provided scratch of M * gemm_tc_kpad(K) floats each.
+int gemm_tc(const float* A, float* A_hi, float* A_lo, int M, int K, const float* Wt_hi, const float* Wt_lo, int N,
+            const float* bias, float* C, int ldc, cudaStream_t stream) {
+  LVSR_CHECK(gemm_tc_supported(M, N, K), "gemm_tc: unsupported shape M=%d N=%d K=%d", M, N, K);
+  if (int rc = get_encode()) return rc;
+  const int Kpad = gemm_tc_kpad(K);
+  if (Kpad == K) {
+    const long long n4 = (long long)M * K / 4;
+    split_tf32_kernel<<<(int)std::min<long long>(4096, (n4 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(A), reinterpret_cast<float4*>(A_hi), reinterpret_cast<float4*>(A_lo), n4);
+  } else {
+    const long long n = (long long)M * Kpad;
+    split_pad_tf32_kernel<<<(int)std::min<long long>(4096, (n + 255) / 256), 256, 0, stream>>>(A, A_hi, A_lo, M, K, Kpad);
+  }
+  LVSR_LAUNCH_CHECK();
+  return gemm_tc_presplit(A_hi, A_lo, M, Wt_hi, Wt_lo, N, Kpad, bias, C, ldc, 1, 0, stream);
 }
 
 }  // namespace lvsr

@@ -30,7 +30,13 @@ inline GemmArgs make_gemm(const float* A, int M, int K, const float* W, int N, c
 
 // ---- gemm_tc.cu: tcgen05 / TMEM / TMA path (3xTF32 split) ------------------------------
 bool gemm_tc_supported(int M, int N, int K);
+int gemm_tc_kpad(int K);                 // contraction dimension as stored in the hi/lo operands (multiple of 32)
 int split_weight_tf32(const float* W, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
+int transpose_split_tf32(const float* W, int K, int N, int ldw, float* hi, float* lo, cudaStream_t stream);
+int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream);
+int gemm_tc_presplit(const float* A_hi, const float* A_lo, int M, const float* B_hi, const float* B_lo, int N, int Kpad,
+                     const float* bias, float* C, int ldc, int splits, long long split_stride, cudaStream_t stream);
+int gemm_tc_splits_launched(int Kpad, int splits);   // how many partial outputs gemm_tc_presplit writes
 int gemm_tc(const float* A, float* A_hi, float* A_lo, int M, int K, const float* Wt_hi, const float* Wt_lo, int N,
             const float* bias, float* C, int ldc, cudaStream_t stream);
 

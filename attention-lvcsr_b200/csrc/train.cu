@@ -87,7 +87,7 @@ int skinny(const float* X0, int K0, int ldx0, const float* W0, const float* X1, 
   a.out = out; a.ldo = ldo; a.R = R; a.N = N;
   dim3 grid(ceil_div(N, SK_N), ceil_div(R, SK_R));
   ProfScope prof("skinny", st);
-  skinny_kernel<<<grid, 256, 0, st>>>(a);
+  skinny_kernel<<<grid, SK_WARPS * 32, 0, st>>>(a);
   LVSR_LAUNCH_CHECK();
   return 0;
 }
@@ -95,6 +95,38 @@ int skinny(const float* X0, int K0, int ldx0, const float* W0, const float* X1, 
 int copy2d(float* dst, int ld_dst, const float* src, int ld_src, int rows, int cols, cudaStream_t st) {
   LVSR_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)ld_dst * sizeof(float), src, (size_t)ld_src * sizeof(float),
                                  (size_t)cols * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// K-major (contraction-major) tf32 hi/lo operand of the tcgen05 GEMM: [rows, Kpad] built from a [K, rows] matrix
+struct TcOperand { float* hi = nullptr; float* lo = nullptr; int rows = 0, Kpad = 0; };
+
+// src [R, cols] (leading dimension ld) -> transposed hi/lo pair [cols, kpad(R)]
+int make_tc_operand(Arena& ws, const float* src, int R, int cols, int ld, TcOperand* out, cudaStream_t st) {
+  out->rows = cols;
+  out->Kpad = gemm_tc_kpad(R);
+  out->hi = ws.f32((size_t)cols * out->Kpad);
+  out->lo = ws.f32((size_t)cols * out->Kpad);
+  LVSR_CHECK(out->hi && out->lo, "out of device memory (tensor-core operand)");
+  return transpose_split_tf32(src, R, cols, ld, out->hi, out->lo, st);
+}
+
+// C[Mo, N] (ldc) (+)= A^T B on the tensor cores: A, B given as K-major operands (rows a0.. / b0..), split-K over the
+// contraction (R) so that every SM gets a tile; partials are summed in a fixed order.
+int gemm_tn_tc(Arena& ws, const TcOperand& A, int a0, int Mo, const TcOperand& B, int b0, int N, float* C, int ldc,
+               bool accumulate, cudaStream_t st) {
+  ProfScope prof("gemm_tn", st);
+  const int tiles = ceil_div(Mo, 128) * (N / 128);
+  const int want = std::max(1, std::min(32, ceil_div(device_sm_count(), tiles)));
+  const int splits = gemm_tc_splits_launched(A.Kpad, want);
+  const size_t mark = ws.off;
+  float* part = ws.f32((size_t)splits * Mo * N);
+  LVSR_CHECK(part, "out of device memory (TN partials)");
+  if (int rc = gemm_tc_presplit(A.hi + (size_t)a0 * A.Kpad, A.lo + (size_t)a0 * A.Kpad, Mo, B.hi + (size_t)b0 * B.Kpad,
+                                B.lo + (size_t)b0 * B.Kpad, N, A.Kpad, nullptr, part, N, want, (long long)Mo * N, st)) return rc;
+  tn_reduce_kernel<<<grid1d((long long)Mo * N), 256, 0, st>>>(part, splits, Mo, N, C, ldc, accumulate ? 1 : 0);
+  LVSR_LAUNCH_CHECK();
+  if (ws.off <= ws.cap) ws.off = mark;
   return 0;
 }
 
@@ -137,8 +169,9 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
     int Tl = T, din = c.num_features;
     for (int l = 0; l < c.num_layers; ++l) {
       const int D = c.dims_bidir[l], Tout = ceil_div(Tl, c.subsample[l]);
-      bytes += ((size_t)Tl * B * 6 * D * 2 + (size_t)(Tl + 2) * B * 2 * D * 2 + (size_t)Tout * B * 2 * D * 2 + (size_t)3 * Tl * B * din) * sizeof(float);
+      bytes += ((size_t)Tl * B * 6 * D * 2 + (size_t)(Tl + 2) * B * 2 * D * 2 + (size_t)Tout * B * 2 * D * 2 + (size_t)3 * Tl * B * gemm_tc_kpad(din)) * sizeof(float);
       bytes += (size_t)80 * std::max(din, 2 * D) * 6 * D * sizeof(float);      // TN partials
+      bytes += ((size_t)2 * (6 * D + din + 3 * D + 32) * (Tl * (size_t)B + 32) + (size_t)2 * Tl * B * 6 * D) * sizeof(float);   // K-major tf32 operands
       Tl = Tout; din = 2 * D;
     }
     bytes += ((size_t)Tp * B * (2 * M + 2 * E) + (size_t)R * (Tp + 8 * C + 3 * E + 2 * M + 3 * Cpm + V + 16) + (size_t)4 * B * Tp +
@@ -164,8 +197,8 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       LVSR_CHECK(tp.pre && tp.hext && tp.out, "out of device memory (encoder tape)");
       if (m->use_tc && l < (int)m->Wcat_hi.size() && m->Wcat_hi[l] && gemm_tc_supported(rows, 6 * D, din)) {
         const size_t mark = ws.off;
-        float* a_hi = ws.f32((size_t)rows * din);
-        float* a_lo = ws.f32((size_t)rows * din);
+        float* a_hi = ws.f32((size_t)rows * gemm_tc_kpad(din));
+        float* a_lo = ws.f32((size_t)rows * gemm_tc_kpad(din));
         LVSR_CHECK(a_hi && a_lo, "out of device memory (tf32 split scratch)");
         if (int rc = gemm_tc(cur, a_hi, a_lo, rows, din, m->Wcat_hi[l], m->Wcat_lo[l], 6 * D, m->bcat[l], tp.pre, 6 * D, st)) return rc;
         if (ws.off <= ws.cap) ws.off = mark;
@@ -442,7 +475,22 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       float* dWcat = ws.f32((size_t)tp.Din * 6 * D);
       float* dbcat = ws.f32((size_t)6 * D);
       LVSR_CHECK(dWcat && dbcat, "out of device memory (fork gradients)");
-      if (int rc = gemm_tn(ws, tp.X, tp.Din, tp.pre, 6 * D, rows, tp.Din, 6 * D, dWcat, 6 * D, false, st)) return rc;
+      // tensor-core path: every operand transposed once into K-major tf32 hi/lo pairs (the contraction runs over the
+      // T*B rows), then five split-K tcgen05 products share them; FFMA tiles for small problems / LVSR_NO_TC_GEMM
+      const bool tc = m->use_tc && rows >= 2048 && D % 128 == 0;
+      TcOperand dPreT, XT, hrT, hpT[2];
+      if (tc) {
+        if (int rc = make_tc_operand(ws, tp.pre, rows, 6 * D, 6 * D, &dPreT, st)) return rc;
+        if (int rc = make_tc_operand(ws, tp.X, rows, tp.Din, tp.Din, &XT, st)) return rc;
+        if (int rc = make_tc_operand(ws, hr, rows, 2 * D, 2 * D, &hrT, st)) return rc;
+        for (int dir = 0; dir < 2; ++dir) {
+          const float* hprev = tp.hext + (size_t)(dir ? 2 : 0) * B * 2 * D + dir * D;
+          if (int rc = make_tc_operand(ws, hprev, rows, D, 2 * D, &hpT[dir], st)) return rc;
+        }
+        if (int rc = gemm_tn_tc(ws, XT, 0, tp.Din, dPreT, 0, 6 * D, dWcat, 6 * D, false, st)) return rc;
+      } else {
+        if (int rc = gemm_tn(ws, tp.X, tp.Din, tp.pre, 6 * D, rows, tp.Din, 6 * D, dWcat, 6 * D, false, st)) return rc;
+      }
       if (int rc = colsum(tp.pre, rows, 6 * D, 6 * D, dbcat, false, st)) return rc;
       for (int dir = 0; dir < 2; ++dir) {
         const std::string b = enc_base(l, dir);
@@ -452,11 +500,16 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
         if (int rc = copy2d(grad_of(m, grads, b + "/fork/fork_inputs.b"), D, dbcat + c0, 6 * D, 1, D, st)) return rc;
         if (int rc = copy2d(grad_of(m, grads, b + "/fork/fork_gate_inputs.b"), 2 * D, dbcat + c0 + D, 6 * D, 1, 2 * D, st)) return rc;
         // recurrent weights: state_to_state = (h*r)^T dA ; state_to_gates = H_prev^T [dGz|dGr]
-        if (int rc = gemm_tn(ws, hr + dir * D, 2 * D, tp.pre + c0, 6 * D, rows, D, D,
-                             grad_of(m, grads, b + "/gatedrecurrent.state_to_state"), D, false, st)) return rc;
-        const float* hprev = tp.hext + (size_t)(dir ? 2 : 0) * B * 2 * D + dir * D;     // slot t (forward) / t+2 (backward)
-        if (int rc = gemm_tn(ws, hprev, 2 * D, tp.pre + c0 + D, 6 * D, rows, D, 2 * D,
-                             grad_of(m, grads, b + "/gatedrecurrent.state_to_gates"), 2 * D, false, st)) return rc;
+        float* gWs = grad_of(m, grads, b + "/gatedrecurrent.state_to_state");
+        float* gWg = grad_of(m, grads, b + "/gatedrecurrent.state_to_gates");
+        if (tc) {
+          if (int rc = gemm_tn_tc(ws, hrT, dir * D, D, dPreT, c0, D, gWs, D, false, st)) return rc;
+          if (int rc = gemm_tn_tc(ws, hpT[dir], 0, D, dPreT, c0 + D, 2 * D, gWg, 2 * D, false, st)) return rc;
+        } else {
+          if (int rc = gemm_tn(ws, hr + dir * D, 2 * D, tp.pre + c0, 6 * D, rows, D, D, gWs, D, false, st)) return rc;
+          const float* hprev = tp.hext + (size_t)(dir ? 2 : 0) * B * 2 * D + dir * D;     // slot t (forward) / t+2 (backward)
+          if (int rc = gemm_tn(ws, hprev, 2 * D, tp.pre + c0 + D, 6 * D, rows, D, 2 * D, gWg, 2 * D, false, st)) return rc;
+        }
         if (int rc = colsum(dh0 + (size_t)dir * B * D, B, D, D, grad_of(m, grads, b + "/gatedrecurrent.initial_state"), false, st)) return rc;
       }
       if (ws.off <= ws.cap) ws.off = mark;
@@ -466,8 +519,21 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       float* dX = ws.f32((size_t)rows * tp.Din);
       float* WcatT = ws.f32((size_t)6 * D * tp.Din);
       LVSR_CHECK(dX && WcatT, "out of device memory (dX)");
-      if (int rc = transpose(m->Wcat[l], WcatT, tp.Din, 6 * D, st)) return rc;
-      if (int rc = gemm_nn(tp.pre, rows, 6 * D, 6 * D, WcatT, tp.Din, tp.Din, nullptr, dX, tp.Din, false, st)) return rc;
+      if (m->use_tc && gemm_tc_supported(rows, tp.Din, 6 * D) && (6 * D) % 32 == 0) {
+        // dX = dPre . Wcat^T: the K-major form of the right-hand side [N = Din, K = 6D] is Wcat itself
+        const size_t mark = ws.off;
+        float* a_hi = ws.f32((size_t)rows * 6 * D);
+        float* a_lo = ws.f32((size_t)rows * 6 * D);
+        float* w_hi = ws.f32((size_t)tp.Din * 6 * D);
+        float* w_lo = ws.f32((size_t)tp.Din * 6 * D);
+        LVSR_CHECK(a_hi && a_lo && w_hi && w_lo, "out of device memory (dX operands)");
+        if (int rc = split_tf32(m->Wcat[l], w_hi, w_lo, (long long)tp.Din * 6 * D, st)) return rc;
+        if (int rc = gemm_tc(tp.pre, a_hi, a_lo, rows, 6 * D, w_hi, w_lo, tp.Din, nullptr, dX, tp.Din, st)) return rc;
+        if (ws.off <= ws.cap) ws.off = mark;
+      } else {
+        if (int rc = transpose(m->Wcat[l], WcatT, tp.Din, 6 * D, st)) return rc;
+        if (int rc = gemm_nn(tp.pre, rows, 6 * D, 6 * D, WcatT, tp.Din, tp.Din, nullptr, dX, tp.Din, false, st)) return rc;
+      }
       dout = dX;
     }
   }

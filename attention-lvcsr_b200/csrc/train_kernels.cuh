@@ -153,10 +153,12 @@ struct SkinnyArgs {
   float* out; int ldo;
   int R, N;
 };
-constexpr int SK_R = 64, SK_N = 8;
+constexpr int SK_R = 64, SK_N = 8, SK_WARPS = 16;
 
-__global__ void __launch_bounds__(256) skinny_kernel(SkinnyArgs a) {
-  __shared__ __align__(16) float red[8][SK_R * SK_N];
+// 64 rows x 8 columns per CTA, K split over 16 warps; two 4-wide k groups are in flight per iteration (the loop is
+// bound by the L2 latency of its operand loads, not by the FMAs).
+__global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(SkinnyArgs a) {
+  __shared__ __align__(16) float red[SK_WARPS][SK_R * SK_N];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * SK_N, r0 = blockIdx.y * SK_R;
   const int rg = lane >> 1, cgp = lane & 1;
@@ -170,17 +172,13 @@ __global__ void __launch_bounds__(256) skinny_kernel(SkinnyArgs a) {
   for (int p = 0; p < 2; ++p) {
     if (a.X[p] == nullptr || c0 >= a.N) continue;
     const int K = a.K[p];
-    const int kq = (K / 4 + 7) / 8;
+    const int kq = (K / 4 + SK_WARPS - 1) / SK_WARPS;
     const int k_lo = min(K, warp * kq * 4), k_hi = min(K, k_lo + kq * 4);
     const float* xr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) xr[i] = a.X[p] + (long long)min(rbase + i, a.R - 1) * a.ldx[p];
-    for (int k = k_lo; k + 4 <= k_hi; k += 4) {
-      float4 xv[4], wv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr[i] + k);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(reinterpret_cast<const float4*>(a.W[p] + (long long)(k + kk) * a.N + c0));
+    const float* wp = a.W[p] + c0;
+    auto fma16 = [&](const float4 (&xv)[4], const float4 (&wv)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
@@ -192,19 +190,40 @@ __global__ void __launch_bounds__(256) skinny_kernel(SkinnyArgs a) {
           acc[i][3] = fmaf(xs[kk], wv[kk].w, acc[i][3]);
         }
       }
+    };
+    int k = k_lo;
+    for (; k + 8 <= k_hi; k += 8) {
+      float4 xa[4], wa[4], xb[4], wb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xa[i] = *reinterpret_cast<const float4*>(xr[i] + k); xb[i] = *reinterpret_cast<const float4*>(xr[i] + k + 4); }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        wa[kk] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(k + kk) * a.N));
+        wb[kk] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(k + 4 + kk) * a.N));
+      }
+      fma16(xa, wa);
+      fma16(xb, wb);
+    }
+    for (; k + 4 <= k_hi; k += 4) {
+      float4 xa[4], wa[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xa[i] = *reinterpret_cast<const float4*>(xr[i] + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) wa[kk] = __ldg(reinterpret_cast<const float4*>(wp + (long long)(k + kk) * a.N));
+      fma16(xa, wa);
     }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(&red[warp][(rg * 4 + i) * SK_N + cgp * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   __syncthreads();
-  for (int o = tid; o < SK_R * SK_N; o += 256) {
+  for (int o = tid; o < SK_R * SK_N; o += SK_WARPS * 32) {
     const int rl = o / SK_N, cl = o % SK_N;
     const int r = r0 + rl, c = n0 + cl;
     if (r >= a.R || c >= a.N) continue;
     float v = 0.f;
 #pragma unroll
-    for (int wq = 0; wq < 8; ++wq) v += red[wq][o];
+    for (int wq = 0; wq < SK_WARPS; ++wq) v += red[wq][o];
     if (a.add[0]) v += a.add[0][(long long)r * a.lda[0] + c];
     if (a.add[1]) v += a.add[1][(long long)r * a.lda[1] + c];
     a.out[(long long)r * a.ldo + c] = v;

@@ -164,3 +164,22 @@ def test_two_gpu_step_equals_single_gpu_step_on_the_concatenated_batch():
                         os.path.join(root, "tests", "dist_train_worker.py")], capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "DIST_TRAIN_OK" in r.stdout
+
+
+def test_gradients_with_tensor_core_backward_gemms(monkeypatch):
+    """T*B >= 2048 rows switches the encoder's weight-gradient (X^T dY, split-K) and input-gradient (dY W^T) GEMMs to
+    the tcgen05 3xTF32 kernel; same bar as the FFMA path, and the two paths agree with each other."""
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    batch = O.synthetic_batch(cfg, B=32, T=64, seed=77)
+    algo, rec = _check_grads(cfg, params, batch)
+    _, g_tc = algo.cost_and_gradients(dict(zip(algo.SOURCES, batch)))
+    monkeypatch.setenv("LVSR_NO_TC_GEMM", "1")
+    pkg = package()
+    rec2 = make_recognizer(cfg, params)
+    algo2 = pkg.GradientDescent(recognizer=rec2, step_rule=pkg.CompositeRule([pkg.RemoveNotFinite(0.0)]))
+    _, g_ff = algo2.cost_and_gradients(dict(zip(algo2.SOURCES, batch)))
+    for k in g_tc:
+        scale = max(np.abs(g_ff[k]).max(), 1e-30)
+        assert np.abs(g_tc[k] - g_ff[k]).max() / scale < 2e-4, k
