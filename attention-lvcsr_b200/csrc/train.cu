@@ -343,8 +343,11 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
   {
     const int tc_cap = ceil_div(Tp, AB_CS);
     const size_t ab_smem = att_bwd_smem_floats(M, E, K, n, tc_cap) * sizeof(float);
-    LVSR_CHECK(ab_smem <= 227 * 1024 && M <= AB_NT && K <= 16 && E % 4 == 0, "attention backward: shape unsupported (Tp=%d M=%d)", Tp, M);
-    LVSR_CUDA_OK(cudaFuncSetAttribute(att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab_smem));
+    LVSR_CHECK(ab_smem <= 227 * 1024 && M <= AB_NT && M % 128 == 0 && K <= 16 && E % 4 == 0,
+               "attention backward: shape unsupported (Tp=%d M=%d)", Tp, M);
+    const bool kp12 = att_bwd_kp(K) == 12;
+    LVSR_CUDA_OK(cudaFuncSetAttribute(att_bwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab_smem));
+    LVSR_CUDA_OK(cudaFuncSetAttribute(att_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab_smem));
     const int ew = ceil_div(B * C, 256);
     for (int i = L - 1; i >= 0; --i) {
       ProfScope prof("dec_bwd_step", st);
@@ -378,7 +381,8 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       ab.B = B; ab.Tp = Tp; ab.M = M; ab.E = E; ab.K = K; ab.n = n;
       {
         ProfScope prof_ab("att_bwd", st);
-        att_bwd_kernel<<<nct, AB_NT, ab_smem, st>>>(ab, tc_cap);
+        if (kp12) att_bwd_kernel<12><<<nct, AB_NT, ab_smem, st>>>(ab, tc_cap);
+        else att_bwd_kernel<16><<<nct, AB_NT, ab_smem, st>>>(ab, tc_cap);
         LVSR_LAUNCH_CHECK();
       }
       // ds_{i-1} = gates/elementwise part + dq . W_s^T (two partials) + readout of step i (which saw s_{i-1})

@@ -451,14 +451,18 @@ struct AttBwdArgs {
   int B, Tp, M, E, K, n;
 };
 
+__host__ __device__ inline int att_bwd_kp(int K) { return K <= 12 ? 12 : 16; }     // padded row of K filter values (float4 loads)
+
 __host__ __device__ inline size_t att_bwd_smem_floats(int M, int E, int K, int n, int tc_cap) {
+  const int KP = att_bwd_kp(K);
   size_t f = 0;
   f += tc_cap + 2 * n + 8;                 // salpha
-  f += (size_t)(2 * n + 1) * K;            // sfilt [j][k]
+  f += 4;                                  // alignment slack
+  f += (size_t)(2 * n + 1) * KP;           // sfilt [j][KP]
   f += (size_t)K * M;                      // sWh
-  f += (size_t)tc_cap * K;                 // sF
-  f += (size_t)tc_cap * K;                 // sdF
-  f += tc_cap;                             // sde
+  f += (size_t)tc_cap * KP;                // sF
+  f += (size_t)tc_cap * KP;                // sdF
+  f += tc_cap + 4;                         // sde
   f += (size_t)AB_TILE * M;                // sdm
   f += E;                                  // sdctx
   f += 64;                                 // block reductions
@@ -477,18 +481,22 @@ __device__ __forceinline__ float block_sum_512(float v, float* scratch) {
   return s;
 }
 
+// KP: padded filter-row length (12 or 16).  Everything indexed by the filter k is held as KP-wide float4 rows so the
+// inner loops are vector shared-memory loads + FMAs; the handler column of a thread lives in registers.
+template <int KP>
 __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_cap) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int KV = KP / 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / AB_CS, rank = blockIdx.x % AB_CS;
   const int M = a.M, E = a.E, K = a.K, n = a.n, w = 2 * n + 1, Tp = a.Tp, B = a.B;
   float* salpha = smem;
-  float* sfilt = salpha + tc_cap + 2 * n + 8;
-  float* sWh = sfilt + (size_t)w * K;
+  float* sfilt = salpha + ((tc_cap + 2 * n + 8 + 3) & ~3);
+  float* sWh = sfilt + (size_t)w * KP;
   float* sF = sWh + (size_t)K * M;
-  float* sdF = sF + (size_t)tc_cap * K;
-  float* sde = sdF + (size_t)tc_cap * K;
-  float* sdm = sde + tc_cap;
+  float* sdF = sF + (size_t)tc_cap * KP;
+  float* sde = sdF + (size_t)tc_cap * KP;
+  float* sdm = sde + ((tc_cap + 3) & ~3);
   float* sdctx = sdm + (size_t)AB_TILE * M;
   float* sred = sdctx + E;
 
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
     const int prel = t0 - n + i;
     salpha[i] = (prel >= 0 && prel < Tw) ? a.w_prev[(long long)b * Tp + b0 + prel] : 0.f;
   }
-  for (int i = tid; i < w * K; i += AB_NT) { const int j = i / K, k = i % K; sfilt[i] = a.filt[(size_t)k * w + j]; }
+  for (int i = tid; i < w * KP; i += AB_NT) { const int j = i / KP, k = i % KP; sfilt[i] = k < K ? a.filt[(size_t)k * w + j] : 0.f; }
   for (int i = tid; i < K * M; i += AB_NT) sWh[i] = a.Wh[i];
   for (int i = tid; i < E; i += AB_NT) sdctx[i] = a.dctx[(long long)b * E + i];
   // S = sum_t alpha_i[t] dalpha_i[t] = dctx . ctx_i + sum_t alpha_i[t] carry[t]
@@ -523,7 +531,8 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
     float d = 0.f;
     for (int e = lane * 4; e < E; e += 128) {
       const float4 h4 = __ldg(reinterpret_cast<const float4*>(hrow + e));
-      d = fmaf(h4.x, sdctx[e], d); d = fmaf(h4.y, sdctx[e + 1], d); d = fmaf(h4.z, sdctx[e + 2], d); d = fmaf(h4.w, sdctx[e + 3], d);
+      const float4 c4 = *reinterpret_cast<const float4*>(sdctx + e);
+      d = fmaf(h4.x, c4.x, d); d = fmaf(h4.y, c4.y, d); d = fmaf(h4.z, c4.z, d); d = fmaf(h4.w, c4.w, d);
     }
     d = warp_sum(d);
     if (lane == 0) {
@@ -532,12 +541,39 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
       sde[t] = a.w_cur[o] * (d + carry - S);
     }
   }
-  // ---- location features of the owned positions: F[t,k] = sum_j alpha_cut[t + n - j] filt[k, j] ----
-  for (int idx = tid; idx < nt * K; idx += AB_NT) {
-    const int t = idx / K, k = idx % K;
-    float acc = 0.f;
-    for (int j = 0; j < w; ++j) acc = fmaf(salpha[t + 2 * n - j], sfilt[j * K + k], acc);
-    sF[idx] = acc;
+  // ---- location features of the owned positions: F[t,k] = sum_j alpha_cut[t + n - j] filt[k, j];
+  //      a position's taps are split over 4 adjacent lanes ----
+  {
+    const int seg = (w + 3) / 4;
+    for (int base = 0; base < nt * 4; base += AB_NT) {
+      const int idx = base + tid, t = idx >> 2, jq = idx & 3;
+      float acc[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+      if (t < nt) {
+        const int j0 = jq * seg, j1 = min(w, j0 + seg);
+        for (int j = j0; j < j1; ++j) {
+          const float av = salpha[t + 2 * n - j];
+          const float4* fr = reinterpret_cast<const float4*>(sfilt + (size_t)j * KP);
+#pragma unroll
+          for (int q = 0; q < KV; ++q) {
+            const float4 f = fr[q];
+            acc[4 * q] = fmaf(av, f.x, acc[4 * q]); acc[4 * q + 1] = fmaf(av, f.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(av, f.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(av, f.w, acc[4 * q + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+      }
+      if (t < nt && jq == 0) {
+#pragma unroll
+        for (int q = 0; q < KV; ++q)
+          *reinterpret_cast<float4*>(sF + (size_t)t * KP + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      }
+    }
   }
   __syncthreads();
 
@@ -545,9 +581,11 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
   const bool col = tid < M;
   const int m = col ? tid : 0;
   const float qm = a.q[(long long)b * M + m], vm = a.v[m];
-  float dq = 0.f, dv = 0.f, dWh[16];
+  float whc[KP], dWh[KP];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) dWh[k] = 0.f;
+  for (int k = 0; k < KP; ++k) { whc[k] = k < K ? sWh[(size_t)k * M + m] : 0.f; dWh[k] = 0.f; }
+  float dq = 0.f, dv = 0.f;
+  const int MQ = M / 128;                       // float4 groups of a handler row per lane in the dF pass
   for (int tile = 0; tile * AB_TILE < nt; ++tile) {
     const int tb = tile * AB_TILE, tn = min(AB_TILE, nt - tb);
     if (col) {
@@ -564,9 +602,13 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
       for (int tl = 0; tl < AB_TILE; ++tl) {
         float dm = 0.f;
         if (tl < tn) {
-          const float* fr = sF + (size_t)(tb + tl) * K;
+          const float4* fr4 = reinterpret_cast<const float4*>(sF + (size_t)(tb + tl) * KP);
+          float fr[KP];
+#pragma unroll
+          for (int q = 0; q < KV; ++q) { const float4 f = fr4[q]; fr[4 * q] = f.x; fr[4 * q + 1] = f.y; fr[4 * q + 2] = f.z; fr[4 * q + 3] = f.w; }
           float f = 0.f;
-          for (int k = 0; k < K; ++k) f = fmaf(fr[k], sWh[(size_t)k * M + m], f);
+#pragma unroll
+          for (int k = 0; k < KP; ++k) f = fmaf(fr[k], whc[k], f);
           const float th = tanhf_acc(pv[tl] + qm + f);
           const float de = sde[tb + tl];
           dm = de * vm * (1.f - th * th);
@@ -574,21 +616,32 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
           dq += dm;
           dv = fmaf(de, th, dv);
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if (k < K) dWh[k] = fmaf(fr[k], dm, dWh[k]);
+          for (int k = 0; k < KP; ++k) dWh[k] = fmaf(fr[k], dm, dWh[k]);
         }
         sdm[(size_t)tl * M + m] = dm;
       }
     }
     __syncthreads();
-    // dF[t, k] = sum_m dmatch[t, m] Wh[k, m]: warp tl, lanes over m
+    // dF[t, k] = sum_m dmatch[t, m] Wh[k, m]: warp tl; lane covers m = 4 lane + 128 q (conflict-free float4 rows)
     if (warp < tn) {
-      const float* dmr = sdm + (size_t)warp * M;
-      for (int k = 0; k < K; ++k) {
+      const float4* dmr = reinterpret_cast<const float4*>(sdm + (size_t)warp * M);
+      float4 dmv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmv[q] = q < MQ ? dmr[q * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* out = sdF + (size_t)(tb + warp) * KP;
+      for (int k = 0; k < KP; ++k) {
         float s = 0.f;
-        for (int mm = lane; mm < M; mm += 32) s = fmaf(dmr[mm], sWh[(size_t)k * M + mm], s);
-        s = warp_sum(s);
-        if (lane == 0) sdF[(size_t)(tb + warp) * K + k] = s;
+        if (k < K) {
+          const float4* wr = reinterpret_cast<const float4*>(sWh + (size_t)k * M);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < MQ) {
+              const float4 w4 = wr[q * 32 + lane];
+              s = fmaf(dmv[q].x, w4.x, s); s = fmaf(dmv[q].y, w4.y, s); s = fmaf(dmv[q].z, w4.z, s); s = fmaf(dmv[q].w, w4.w, s);
+            }
+          s = warp_sum(s);
+        }
+        if (lane == 0) out[k] = s;
       }
     }
     __syncthreads();
@@ -598,29 +651,53 @@ __global__ void __launch_bounds__(AB_NT, 1) att_bwd_kernel(AttBwdArgs a, int tc_
     a.dq_part[((long long)rank * B + b) * M + m] = dq;
     a.acc_v[(long long)blockIdx.x * M + m] += dv;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < KP; ++k)
       if (k < K) a.acc_Wh[((long long)blockIdx.x * K + k) * M + m] += dWh[k];
   }
-  // gradient of alpha_{i-1}: dalpha_cut[t'] = sum_k sum_j dF[t' - n + j, k] filt[k, j] over the OWNED t = t' - n + j
+  // gradient of alpha_{i-1}: dalpha_cut[t'] = sum_j dF[t' - n + j, :] . filt[:, j] over the OWNED t = t' - n + j
   for (int pidx = tid; pidx < Tp; pidx += AB_NT) {
     float acc = 0.f;
     const int tp = pidx - b0;                      // window-relative position of the output
     if (tp >= 0 && tp < Tw && nt > 0) {
       const int jlo = max(0, t0 - tp + n), jhi = min(w - 1, t1 - 1 - tp + n);
       for (int j = jlo; j <= jhi; ++j) {
-        const float* dfr = sdF + (size_t)(tp - n + j - t0) * K;
-        const float* fj = sfilt + (size_t)j * K;
-        for (int k = 0; k < K; ++k) acc = fmaf(dfr[k], fj[k], acc);
+        const float4* dfr = reinterpret_cast<const float4*>(sdF + (size_t)(tp - n + j - t0) * KP);
+        const float4* fj = reinterpret_cast<const float4*>(sfilt + (size_t)j * KP);
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+          const float4 d4 = dfr[q], f4 = fj[q];
+          acc = fmaf(d4.x, f4.x, acc); acc = fmaf(d4.y, f4.y, acc); acc = fmaf(d4.z, f4.z, acc); acc = fmaf(d4.w, f4.w, acc);
+        }
       }
     }
     a.dA_out[((long long)rank * B + b) * Tp + pidx] = acc;
   }
-  // dfilt[k, j] += sum_t dF[t, k] alpha_cut[t + n - j]
-  for (int idx = tid; idx < K * w; idx += AB_NT) {
-    const int k = idx / w, j = idx % w;
-    float acc = 0.f;
-    for (int t = 0; t < nt; ++t) acc = fmaf(sdF[(size_t)t * K + k], salpha[t + 2 * n - j], acc);
-    a.acc_filt[(long long)blockIdx.x * K * w + idx] += acc;
+  // dfilt[k, j] += sum_t dF[t, k] alpha_cut[t + n - j]: a tap's positions are split over 2 adjacent lanes
+  for (int base = 0; base < 2 * w; base += AB_NT) {
+    const int idx = base + tid, j = idx >> 1, th = idx & 1;
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
+    if (j < w) {
+      const int half = (nt + 1) / 2, ta = th * half, tb2 = min(nt, ta + half);
+      for (int t = ta; t < tb2; ++t) {
+        const float av = salpha[t + 2 * n - j];
+        const float4* dfr = reinterpret_cast<const float4*>(sdF + (size_t)t * KP);
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+          const float4 d4 = dfr[q];
+          acc[4 * q] = fmaf(av, d4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(av, d4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(av, d4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(av, d4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    if (j < w && th == 0) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        if (k < K) a.acc_filt[(long long)blockIdx.x * K * w + (size_t)k * w + j] += acc[k];
+    }
   }
 }
 
