@@ -40,6 +40,8 @@ class LvsrConfig(C.Structure):
         ("prior_max_speed", C.c_double),
         ("prior_before", C.c_double),
         ("prior_after", C.c_double),
+        ("one_of_n_feedback", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

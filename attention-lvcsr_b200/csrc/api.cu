@@ -88,7 +88,7 @@ void build_param_table(lvsr_model* m) {
   const int E = m->E, C = c.dim_dec, M = c.dim_matcher, K = c.conv_num_filters, w = 2 * c.conv_n + 1;
   const int V = c.num_phonemes, Cfb = c.dim_feedback, Cpm = c.post_merge_dim;
   const std::string g = GEN, t = TR, a = ATT;
-  add_param(m, g + "/readout/lookupfeedback/lookuptable.W", V + 1, Cfb);
+  if (!c.one_of_n_feedback) add_param(m, g + "/readout/lookupfeedback/lookuptable.W", V + 1, Cfb);
   if (c.use_states_for_readout) add_param(m, g + "/readout/merge/transform_states.W", C, Cpm);
   add_param(m, g + "/readout/merge/transform_weighted_averages.W", E, Cpm);
   add_param(m, g + "/readout/post_merge/bias.b", Cpm);
@@ -168,7 +168,7 @@ int transition(lvsr_model* m, int R, const float* states, const float* ctx, cons
   DenseArgs g = {};
   g.X1 = ctx; g.K1 = m->E; g.W1 = m->Wd_cat;
   g.X2 = states; g.K2 = C; g.W2 = m->P(std::string(TR) + "/transition.state_to_gates"); g.N2 = 2 * C;
-  g.add = m->FF; g.arow = outputs; g.R = R; g.N = 3 * C; g.mode = DENSE_GATES;
+  g.add = m->FF; g.arow = outputs; g.add_rows = c.num_phonemes + 1; g.R = R; g.N = 3 * C; g.mode = DENSE_GATES;
   g.s = states; g.z = z; g.hr = hr; g.ai = ai; g.C = C;
   if (int rc = dense_step(g, st)) return rc;
   DenseArgs k = {};
@@ -272,7 +272,8 @@ int lvsr_model_create(const lvsr_config* cfg, lvsr_model** out) {
   LVSR_CHECK(cfg->dim_dec % 8 == 0 && cfg->post_merge_dim % 8 == 0, "dim_dec and post_merge_dim must be multiples of 8");
   LVSR_CHECK(cfg->dim_matcher == 128 || cfg->dim_matcher == 256 || cfg->dim_matcher == 512,
              "dim_matcher %d unsupported by the attention kernel (128, 256 or 512)", cfg->dim_matcher);
-  LVSR_CHECK(cfg->dim_feedback % 4 == 0, "dim_feedback must be a multiple of 4");
+  LVSR_CHECK(cfg->one_of_n_feedback ? cfg->dim_feedback == cfg->num_phonemes + 1 : cfg->dim_feedback % 4 == 0,
+             "dim_feedback must be a multiple of 4 (LookupFeedback) or num_phonemes + 1 (OneOfNFeedback)");
   LVSR_CHECK(cfg->maxout_pieces >= 1 && cfg->post_merge_dim % cfg->maxout_pieces == 0, "bad maxout_pieces");
   LVSR_CHECK(cfg->post_merge_activation >= LVSR_ACT_MAXOUT && cfg->post_merge_activation <= LVSR_ACT_IDENTITY,
              "bad post_merge_activation");
@@ -481,9 +482,14 @@ int finalize_on_stream(lvsr_model* m, cudaStream_t st, bool synchronise) {
         return rc;
   }
   // fork(feedback(y)) for every symbol y, once: [(V+1), 3C]
-  GemmArgs ff = make_gemm(m->P(g + "/readout/lookupfeedback/lookuptable.W"), V + 1, Cfb, m->Wff_cat, 3 * C,
-                          m->bff_cat, m->FF);
-  if (int rc = gemm_bias(ff, st)) return rc;
+  if (c.one_of_n_feedback) {
+    // one-hot feedback: fork(feedback(y)) is row y of the fork weights plus the bias
+    if (int rc = add_bias_rows(m->FF, m->Wff_cat, m->bff_cat, V + 1, 3 * C, st)) return rc;
+  } else {
+    GemmArgs ff = make_gemm(m->P(g + "/readout/lookupfeedback/lookuptable.W"), V + 1, Cfb, m->Wff_cat, 3 * C,
+                            m->bff_cat, m->FF);
+    if (int rc = gemm_bias(ff, st)) return rc;
+  }
   m->v_bias = 0.f;
   if (c.energy_normalizer != LVSR_NORM_SOFTMAX)
     LVSR_CUDA_OK(cudaMemcpy(&m->v_bias, m->P(std::string(ATT) + "/energy_comp/linear.b"), sizeof(float),
@@ -620,6 +626,7 @@ int lvsr_cost_matrix(lvsr_model* m, const float* attended, const float* attended
     d.status = m->status;
     d.Tp = Tp; d.B = B; d.L = L; d.M = M; d.E = E; d.C = C; d.K = c.conv_num_filters; d.n = c.conv_n;
     d.normalizer = c.energy_normalizer;
+    d.V = c.num_phonemes;
     // per-step hand-over buffers of the data-flow decoder; everything another CTA polls starts
     // as the sentinel (0xFF bytes)
     d.w_all = weights_out ? weights_out : ws.f32((size_t)L * B * Tp);

@@ -96,7 +96,8 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float
 // and <256, 4 CTAs, 16 warps> = 512 threads, one CTA per SM.  At the metric batch the second wins:
 // with two clusters sharing every SM any stall of one CTA delays its whole 8-CTA cluster twice per
 // step (1.73 us per step when a narrow CTA owns its SM vs 3.07 us when two share one).
-template <int D, int CS, int NWARP>
+// TAPE: training forward (stores c / z / r over the pre-activations and every frame of h); compiled out for inference
+template <int D, int CS, int NWARP, bool TAPE>
 __global__ void __launch_bounds__(NWARP * 32, NWARP == 8 ? 2 : 1)
 bigru_kernel(BiGruArgs a) {
   constexpr int UC = D / CS;          // units owned by this CTA
@@ -200,7 +201,7 @@ bigru_kernel(BiGruArgs a) {
   }
   float h_own = h0[u_warp + unit2];                                        // h(row2, unit2), same for every row at t = -1
   // training tape: broadcast initial state into its boundary slot of hext
-  if (a.hext != nullptr) {
+  if constexpr (TAPE) {
     for (int i = tid; i < RB * UC; i += NWARP * 32) {
       const int r = i / UC, u = rank * UC + i % UC;
       if (row0 + r < a.B)
@@ -219,8 +220,8 @@ bigru_kernel(BiGruArgs a) {
   const float* pa_ptr = pre_dir + ((long long)t * B + row0 + row2) * pre_ld + u_warp + unit2;
   const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + row2 : nullptr;
   // tape slots of this lane's gate / candidate (same addresses the pre-activations are read from)
-  float* tg_ptr = a.tape ? a.tape + (pg_ptr - a.pre) : nullptr;
-  float* ta_ptr = a.tape ? a.tape + (pa_ptr - a.pre) : nullptr;
+  float* tg_ptr = TAPE ? a.tape + (pg_ptr - a.pre) : nullptr;
+  float* ta_ptr = TAPE ? a.tape + (pa_ptr - a.pre) : nullptr;
   const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
   float pg = 0.f, pa = 0.f, pm = 1.f;
   auto prefetch = [&]() {
@@ -291,7 +292,7 @@ bigru_kernel(BiGruArgs a) {
     BG_STAMP(1);
     warp_reduce_scatter<N1, CG>(acc1, lane);
     const float gate = fast_sigmoid(acc1[0] + g_cur);                    // z or r of (row1, unit1)
-    if (tg_ptr != nullptr) {
+    if constexpr (TAPE) {
       if (ok1) *tg_ptr = gate;
       tg_ptr += pre_step;
     }
@@ -336,7 +337,7 @@ bigru_kernel(BiGruArgs a) {
     {
       const float zg = __shfl_sync(0xffffffffu, gate, src_z);            // update gate of (row2, unit2)
       const float cand = fast_tanh(acc2[0] + a_cur);
-      if (ta_ptr != nullptr) {
+      if constexpr (TAPE) {
         if (ok2 && (kg & 1) == 0) *ta_ptr = cand;       // the lane pair kg, kg ^ 1 holds the same value
         ta_ptr += pre_step;
       }
@@ -349,7 +350,7 @@ bigru_kernel(BiGruArgs a) {
       if (sub_phase == 0 && peer == 0 && row0 + rowg < B)
         *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
             make_float4(x, y, z, w);
-      if (a.hext != nullptr && peer == 0 && row0 + rowg < B)
+      if (TAPE && peer == 0 && row0 + rowg < B)
         *reinterpret_cast<float4*>(a.hext + ((long long)(t + 1) * B + row0 + rowg) * (2 * D) + dir * D + u_warp) =
             make_float4(x, y, z, w);
     }
@@ -372,13 +373,13 @@ bigru_kernel(BiGruArgs a) {
   cluster_sync_all();
 }
 
-template <int D, int CS, int NWARP>
-int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
+template <int D, int CS, int NWARP, bool TAPE>
+int launch_bigru_t(const BiGruArgs& a, cudaStream_t stream) {
   constexpr size_t W2S_BYTES = (size_t)NWARP * (D / 16 / 4) * 2 * 32 * 4 * sizeof(float);
   static bool configured[LVSR_MAX_DEVICES] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_kernel<D, CS, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_kernel<D, CS, NWARP, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)W2S_BYTES));
     configured[dev] = true;
   }
@@ -400,7 +401,7 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
     const int on = 1;
     LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_bigru_trace_on, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream));
   }
-  LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_kernel<D, CS, NWARP>, a));
+  LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_kernel<D, CS, NWARP, TAPE>, a));
   g_launch_count++;
   if (trace) {
     unsigned long long h[8] = {0};
@@ -415,6 +416,12 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+template <int D, int CS, int NWARP>
+int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
+  LVSR_CHECK((a.tape == nullptr) == (a.hext == nullptr), "bigru: tape and hext go together");
+  return a.tape ? launch_bigru_t<D, CS, NWARP, true>(a, stream) : launch_bigru_t<D, CS, NWARP, false>(a, stream);
+}
+
 int bigru_sm_count() { return device_sm_count(); }
 
 // how many <256, 4, 16> clusters the device holds at once (a GPC takes floor(SMs / 4) of them; the
@@ -427,7 +434,7 @@ int wide_clusters_resident() {
   if (!known[dev]) {
     known[dev] = true;
     constexpr size_t W2S_BYTES = (size_t)16 * (256 / 16 / 4) * 2 * 32 * 4 * sizeof(float);
-    cudaFuncSetAttribute(bigru_kernel<256, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2S_BYTES);
+    cudaFuncSetAttribute(bigru_kernel<256, 4, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W2S_BYTES);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(4 * 64);
     cfg.blockDim = dim3(16 * 32);
@@ -440,7 +447,7 @@ int wide_clusters_resident() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int k = 0;
-    if (cudaOccupancyMaxActiveClusters(&k, bigru_kernel<256, 4, 16>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&k, bigru_kernel<256, 4, 16, false>, &cfg) != cudaSuccess) {
       cudaGetLastError();
       k = 0;
     }

@@ -47,6 +47,7 @@ struct DenseIO {
   int C;
   const float* add;             // [*, N] addend
   const long long* arow;        // row index into add (or null: identity)
+  long long add_rows;           // rows of the addend table (labels are clamped into it)
   float* hr;                    // EP_GATES: reset-gated state [R, C], consumed by every candidate tile
   float* loc;                   // smem [3][DS_ROWS][ncu]: update gate, candidate input, state of this tile's units
   int ncu;                      // units per tile (EP_GATES / EP_CAND)
@@ -87,6 +88,7 @@ __device__ __noinline__ void dense_tile(const DenseIO& d, const float* ws, int w
         if (gate < 3 && u < d.C) {
           long long lab;
           asm volatile("ld.global.nc.s64 %0, [%1];\n" : "=l"(lab) : "l"(d.arow + r));
+          lab = lab < 0 ? 0 : (lab > d.add_rows - 1 ? d.add_rows - 1 : lab);     // device labels are not range-checked by the API: never index outside the table
           asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(ep_pref) : "l"(d.add + lab * 3 * d.C + gate * d.C + u));
         }
       } else if (d.mode == EP_CAND) {
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
     if (in1) {
       DenseIO d = {};
       d.X1 = ctx_cur; d.K1 = E; d.X2 = s_cur; d.K2 = C; d.R = Rlim; d.N = 3 * C; d.mode = EP_GATES; d.C = C;
-      d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.hr = hr_cur; d.loc = loc; d.ncu = a.nc2;
+      d.add = a.FF; d.arow = a.labels + (size_t)i * R; d.add_rows = a.V + 1; d.hr = hr_cur; d.loc = loc; d.ncu = a.nc2;
       d.tr = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)a.L * 8 + (size_t)i * 4 : nullptr;
       dense_dispatch(a.nc1 / 8, d, w1s, ws1, r0, cgi * a.nc2, red);
     }

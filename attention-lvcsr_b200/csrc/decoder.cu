@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseArgs a) {
 #pragma unroll
     for (int wq = 0; wq < 8; ++wq) v += red[wq][o];
     if (a.add) {
-      const long long ar = a.arow ? a.arow[r] : (long long)r;
+      long long ar = a.arow ? a.arow[r] : (long long)r;
+      if (a.arow && a.add_rows > 0) ar = ar < 0 ? 0 : (ar > a.add_rows - 1 ? a.add_rows - 1 : ar);
       v += a.add[ar * a.N + c];
     }
     if (a.mode == DENSE_PLAIN) {
@@ -179,6 +180,9 @@ __global__ void fill_i64_kernel(long long* p, long long n, long long v) {
 }
 __global__ void broadcast_rows_kernel(float* dst, const float* src, long long total, int N) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i % N];
+}
+__global__ void add_bias_rows_kernel(float* dst, const float* src, const float* bias, long long total, int N) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i] + bias[i % N];
 }
 __global__ void onehot_rows_kernel(float* dst, long long total, int N) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) dst[i] = (i % N == 0) ? 1.f : 0.f;
@@ -309,6 +313,13 @@ int broadcast_rows(float* dst, const float* src, int R, int N, cudaStream_t stre
   const long long total = (long long)R * N;
   if (total <= 0) return 0;
   broadcast_rows_kernel<<<grid_for(total), 256, 0, stream>>>(dst, src, total, N);
+  LVSR_LAUNCH_CHECK();
+  return 0;
+}
+int add_bias_rows(float* dst, const float* src, const float* bias, int R, int N, cudaStream_t stream) {
+  const long long total = (long long)R * N;
+  if (total <= 0) return 0;
+  add_bias_rows_kernel<<<grid_for(total), 256, 0, stream>>>(dst, src, bias, total, N);
   LVSR_LAUNCH_CHECK();
   return 0;
 }

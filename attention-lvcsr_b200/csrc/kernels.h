@@ -125,6 +125,7 @@ struct DenseArgs {
   const float* X2; int K2; const float* W2; int N2; // W2 [K2, N2], may be null
   const float* add;        // [*, N] addend rows or nullptr
   const long long* arow;   // [R] row index into add (labels) or nullptr (identity)
+  long long add_rows;      // rows of `add` when arow is given (0 = unknown): indices are clamped into the table
   int R, N, mode;
   // DENSE_PLAIN: out[R,N]
   float* out;
@@ -179,6 +180,7 @@ struct DecScanArgs {
   unsigned long long* trace;           // optional debug stamps, or nullptr
   unsigned* status;                    // launch status word (common.cuh: LVSR_FLOW_*), zeroed by the caller
   int Tp, B, L, M, E, C, K, n, normalizer;
+  int V;                               // num_phonemes: the feedback table FF has V + 1 rows
   // derived by the planner
   int cs, tc_cap, nrg, nc1, nc2, nc3;
   int nisl, ncg;                       // nisl > 0: islands of <= 16 rows whose CTAs own their dense tiles
@@ -196,6 +198,7 @@ int gather_i64(long long* dst, const long long* src, const int* idx, int Rn, lon
 // k smallest of cost_so_far[r] + neglogp[r, v] over the rows of each segment (B/search.py:341-344)
 int segment_topk(const float* neglogp, const float* cost_so_far, const int* seg_start, int nseg, int V, int k,
                  int* top_parent, int* top_symbol, float* top_cost, int* top_count, cudaStream_t stream);
+int add_bias_rows(float* dst, const float* src, const float* bias, int R, int N, cudaStream_t stream);   // dst[r,:] = src[r,:] + bias
 int add_i64(long long* dst, const long long* src, int n, long long inc, cudaStream_t stream);
 int gather_time_subsample(float* dst, const float* src, int Tout, int k, long long row_elems,
                           cudaStream_t stream);                                         // dst[t] = src[t*k]

@@ -18,6 +18,15 @@ struct Arena {
   size_t cap = 0, off = 0, overflow_bytes = 0;
   int depth = 0;
   std::vector<void*> overflow;
+  // the arena is rewound when a call returns while its kernels may still be in flight: safe only if the next call
+  // is enqueued on the SAME stream.  A call on another stream first waits for everything the previous one enqueued.
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
+  void bind_stream(cudaStream_t st) {
+    if (depth == 0 && used && st != last_stream) cudaStreamSynchronize(last_stream);
+    last_stream = st;
+    used = true;
+  }
 
   void* alloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
@@ -172,8 +181,8 @@ struct DeviceGuard {
 struct ArenaScope {
   Arena& ws;
   cudaStream_t st;
-  ArenaScope(lvsr_model* mm, cudaStream_t s) : ws(mm->ws), st(s) { ws.enter(); }
-  ArenaScope(Arena& a, cudaStream_t s) : ws(a), st(s) { ws.enter(); }
+  ArenaScope(lvsr_model* mm, cudaStream_t s) : ws(mm->ws), st(s) { ws.bind_stream(s); ws.enter(); }
+  ArenaScope(Arena& a, cudaStream_t s) : ws(a), st(s) { ws.bind_stream(s); ws.enter(); }
   ~ArenaScope() { ws.leave(st); }
 };
 

@@ -425,10 +425,15 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
     LVSR_CHECK(dFF && WffT && dlook && dWff && dbff, "out of device memory (feedback gradients)");
     scatter_rows_kernel<<<V + 1, 256, 0, st>>>(dG, lab, R, 3 * C, dFF);
     LVSR_LAUNCH_CHECK();
-    if (int rc = transpose(m->Wff_cat, WffT, Cfb, 3 * C, st)) return rc;
-    const float* look = m->P(g + "/readout/lookupfeedback/lookuptable.W");
-    if (int rc = gemm_nn(dFF, V + 1, 3 * C, 3 * C, WffT, Cfb, Cfb, nullptr, grad_of(m, grads, g + "/readout/lookupfeedback/lookuptable.W"), Cfb, false, st)) return rc;
-    if (int rc = gemm_tn(ws, look, Cfb, dFF, 3 * C, V + 1, Cfb, 3 * C, dWff, 3 * C, false, st)) return rc;
+    if (c.one_of_n_feedback) {
+      // FF[y] = W_fork[y, :] + b: the gradient of the fork weights IS dFF
+      LVSR_CUDA_OK(cudaMemcpyAsync(dWff, dFF, (size_t)(V + 1) * 3 * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (int rc = transpose(m->Wff_cat, WffT, Cfb, 3 * C, st)) return rc;
+      const float* look = m->P(g + "/readout/lookupfeedback/lookuptable.W");
+      if (int rc = gemm_nn(dFF, V + 1, 3 * C, 3 * C, WffT, Cfb, Cfb, nullptr, grad_of(m, grads, g + "/readout/lookupfeedback/lookuptable.W"), Cfb, false, st)) return rc;
+      if (int rc = gemm_tn(ws, look, Cfb, dFF, 3 * C, V + 1, Cfb, 3 * C, dWff, 3 * C, false, st)) return rc;
+    }
     if (int rc = colsum(dFF, V + 1, 3 * C, 3 * C, dbff, false, st)) return rc;
     // Wff_cat columns: [gate_inputs 2C | inputs C]
     if (int rc = copy2d(grad_of(m, grads, g + "/fork/fork_gate_inputs.W"), 2 * C, dWff, 3 * C, Cfb, 2 * C, st)) return rc;

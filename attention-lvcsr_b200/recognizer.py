@@ -79,8 +79,6 @@ class SpeechRecognizer(object):
             unsupported("dims_top")
         if dec_stack != 1:
             unsupported("dec_stack > 1")
-        if not embed_outputs:
-            unsupported("embed_outputs=False (OneOfNFeedback)")
         if criterion is not None and criterion.get("name", "log_likelihood") != "log_likelihood":
             unsupported("criterion %r" % criterion.get("name"))
         if bottom and bottom.get("dims"):
@@ -114,7 +112,10 @@ class SpeechRecognizer(object):
             num_features=int(input_dims["recordings"]), dims_bidir=[int(d) for d in dims_bidir],
             subsample=[int(k) for k in subsample], dim_dec=int(dim_dec), dim_matcher=int(dim_matcher),
             conv_n=int(conv_n), conv_num_filters=int(conv_num_filters), num_phonemes=int(num_phonemes),
-            dim_feedback=int(dim_dec if dim_output_embedding is None else dim_output_embedding),
+            # LookupFeedback(V+1, dim) or OneOfNFeedback(V+1) whose feedback is the one-hot vector (recognizer.py:278-284)
+            dim_feedback=(int(dim_dec if dim_output_embedding is None else dim_output_embedding) if embed_outputs
+                          else int(num_phonemes) + 1),
+            embed_outputs=bool(embed_outputs),
             post_merge_dim=int(post_merge_dims[0]) if post_merge_dims else int(num_phonemes),
             post_merge_activation=act.kind, maxout_pieces=int(getattr(act, "num_pieces", 1)),
             use_states_for_readout=bool(use_states_for_readout),
@@ -193,6 +194,7 @@ class SpeechRecognizer(object):
         cfg.prior_max_speed = float(p.get("max_speed", 0))
         cfg.prior_before = float(p.get("before", 0))
         cfg.prior_after = float(p.get("after", 0))
+        cfg.one_of_n_feedback = 0 if n.get("embed_outputs", True) else 1
         return cfg
 
     def _require_ready(self):

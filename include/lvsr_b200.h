@@ -57,6 +57,10 @@ typedef struct {
   int32_t prior_type;              /* LVSR_PRIOR_*                                     */
   double prior_initial_begin, prior_initial_end, prior_min_speed, prior_max_speed;
   double prior_before, prior_after;
+  int32_t one_of_n_feedback;       /* 0: LookupFeedback(V+1, dim_feedback) (embed_outputs=True, the default);
+                                      1: OneOfNFeedback(V+1) (embed_outputs=False, lvsr/bricks/__init__.py:86-109;
+                                      exp/wsj/configs/wsj_jan_new.yaml:46): feedback = one-hot, dim_feedback = V+1  */
+  int32_t reserved;
 } lvsr_config;
 
 const char* lvsr_last_error(void);

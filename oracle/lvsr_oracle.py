@@ -159,7 +159,7 @@ def make_config(num_features=40, dims_bidir=(256, 256, 256, 256), subsample=None
                 dim_output_embedding=None, prior=None, energy_normalizer="softmax",
                 attention_type="content_and_conv", eos_label=None,
                 max_decoded_length_scale=1.0, use_states_for_readout=True,
-                post_merge_activation=None):
+                post_merge_activation=None, embed_outputs=True):
     """The subset of ``config['net']`` the hot path depends on
     (lvsr/bricks/recognizer.py:176-204)."""
     dims_bidir = list(dims_bidir)
@@ -174,7 +174,10 @@ def make_config(num_features=40, dims_bidir=(256, 256, 256, 256), subsample=None
         post_merge_dims=list(post_merge_dims) if post_merge_dims else [int(dim_dec)],
         maxout_pieces=int(maxout_pieces) if (post_merge_activation in (None, "maxout")) else 1,
         post_merge_activation=(post_merge_activation or ("maxout" if maxout_pieces > 1 else "relu")),
-        dim_feedback=int(dim_output_embedding if dim_output_embedding is not None else dim_dec),
+        # LookupFeedback(V+1, dim) | OneOfNFeedback(V+1): the feedback is the one-hot vector (recognizer.py:278-284)
+        dim_feedback=(int(dim_output_embedding if dim_output_embedding is not None else dim_dec) if embed_outputs
+                      else int(num_phonemes) + 1),
+        embed_outputs=bool(embed_outputs),
         prior=dict(prior) if prior else dict(DEFAULT_PRIOR),
         energy_normalizer=energy_normalizer or "softmax",
         attention_type=attention_type,
@@ -215,7 +218,8 @@ def param_shapes(cfg):
     V, Cfb, Cpm = cfg["num_phonemes"], cfg["dim_feedback"], cfg["post_merge_dims"][0]
     g = "/recognizer/generator"
     # generator.children = [readout, fork, transition] (B/bricks/sequence_generators.py:157)
-    shapes[g + "/readout/lookupfeedback/lookuptable.W"] = (V + 1, Cfb)
+    if cfg.get("embed_outputs", True):
+        shapes[g + "/readout/lookupfeedback/lookuptable.W"] = (V + 1, Cfb)
     if cfg["use_states_for_readout"]:
         shapes[g + "/readout/merge/transform_states.W"] = (C, Cpm)
     shapes[g + "/readout/merge/transform_weighted_averages.W"] = (E, Cpm)
@@ -480,7 +484,10 @@ def compute_states(cfg, params, states, inputs, gate_inputs, weighted_averages, 
 def feedback_fork(cfg, params, outputs):
     """readout.feedback (LookupFeedback, B/bricks/sequence_generators.py:839-842)
     followed by generator.fork (Linear+bias each)."""
-    fb = params[_GEN + "/readout/lookupfeedback/lookuptable.W"][outputs]
+    if cfg.get("embed_outputs", True):
+        fb = params[_GEN + "/readout/lookupfeedback/lookuptable.W"][outputs]
+    else:       # OneOfNFeedback.feedback, lvsr/bricks/__init__.py:97-104: eye(V+1)[outputs]
+        fb = np.eye(cfg["num_phonemes"] + 1, dtype=params[_GEN + "/fork/fork_inputs.W"].dtype)[outputs]
     inputs = linear(fb, params[_GEN + "/fork/fork_inputs.W"], params[_GEN + "/fork/fork_inputs.b"])
     gate_inputs = linear(fb, params[_GEN + "/fork/fork_gate_inputs.W"],
                          params[_GEN + "/fork/fork_gate_inputs.b"])

@@ -129,7 +129,10 @@ def _cost_matrix(cfg, p, attended, attended_mask, labels, labels_mask):
     torch = _torch()
     L, B = labels.shape
     P = attended @ p[_ATT + "/preprocess.W"] + p[_ATT + "/preprocess.b"]
-    fb = p[_GEN + "/readout/lookupfeedback/lookuptable.W"][torch.as_tensor(labels)]
+    if cfg.get("embed_outputs", True):
+        fb = p[_GEN + "/readout/lookupfeedback/lookuptable.W"][torch.as_tensor(labels)]
+    else:
+        fb = torch.eye(cfg["num_phonemes"] + 1, dtype=attended.dtype)[torch.as_tensor(labels)]
     inputs = fb @ p[_GEN + "/fork/fork_inputs.W"] + p[_GEN + "/fork/fork_inputs.b"]
     gate_inputs = fb @ p[_GEN + "/fork/fork_gate_inputs.W"] + p[_GEN + "/fork/fork_gate_inputs.b"]
     s = p[_TR + "/transition.initial_state"][None, :].expand(B, -1)

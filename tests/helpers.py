@@ -25,7 +25,8 @@ def make_recognizer(cfg, params=None):
         num_phonemes=cfg["num_phonemes"], dim_dec=cfg["dim_dec"], dims_bidir=cfg["dims_bidir"],
         subsample=cfg["subsample"], conv_n=cfg["conv_n"], conv_num_filters=cfg["conv_num_filters"],
         dim_matcher=cfg["dim_matcher"], post_merge_dims=cfg["post_merge_dims"], post_merge_activation=act,
-        dim_output_embedding=cfg["dim_feedback"], prior=cfg["prior"], energy_normalizer=cfg["energy_normalizer"],
+        dim_output_embedding=cfg["dim_feedback"] if cfg.get("embed_outputs", True) else None,
+        embed_outputs=cfg.get("embed_outputs", True), prior=cfg["prior"], energy_normalizer=cfg["energy_normalizer"],
         use_states_for_readout=cfg["use_states_for_readout"],
         max_decoded_length_scale=cfg["max_decoded_length_scale"],
         enc_transition=pkg.GatedRecurrent, dec_transition=pkg.GatedRecurrent, data_prepend_eos=False)

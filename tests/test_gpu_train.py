@@ -183,3 +183,16 @@ def test_gradients_with_tensor_core_backward_gemms(monkeypatch):
     for k in g_tc:
         scale = max(np.abs(g_ff[k]).max(), 1e-30)
         assert np.abs(g_tc[k] - g_ff[k]).max() / scale < 2e-4, k
+
+
+def test_one_of_n_feedback_cost_and_gradients():
+    """embed_outputs=False (the WSJ configs): no lookup table, fork weights indexed by the label."""
+    _torch()
+    cfg = O.make_config(embed_outputs=False, **PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    assert "/recognizer/generator/fork/fork_inputs.W" in params and params["/recognizer/generator/fork/fork_inputs.W"].shape == (33, 128)
+    batch = O.synthetic_batch(cfg, B=5, T=48, seed=9)
+    algo, rec = _check_grads(cfg, params, batch)
+    want = O.recognizer_cost(cfg, params, *batch)
+    got = rec.cost(*batch)
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()

@@ -292,3 +292,18 @@ def test_gru_many_steps_masked_through_encoder():
     cfg2 = dict(cfg, subsample=[3])
     sub, sub_mask = O.encoder(cfg2, params, x, mask, activation=np.tanh, gate_activation=np.tanh)
     assert_allclose(sub, got[::3]); assert_allclose(sub_mask, mask[::3])
+
+
+def test_one_of_n_feedback_is_a_lookup_of_the_identity():
+    """embed_outputs=False (OneOfNFeedback, lvsr/bricks/__init__.py:86-109; exp/wsj/configs/wsj_jan_new.yaml:46) ==
+    LookupFeedback whose table is the identity: the pinned cost_matrix path covers it."""
+    base = dict(num_features=4, dims_bidir=[3], dim_dec=6, dim_matcher=6, conv_n=2, conv_num_filters=2, num_phonemes=5,
+                post_merge_dims=[6], maxout_pieces=2)
+    cfg1 = O.make_config(embed_outputs=False, **base)
+    cfg2 = O.make_config(dim_output_embedding=6, **base)          # V + 1 = 6
+    assert cfg1["dim_feedback"] == 6 and "/recognizer/generator/readout/lookupfeedback/lookuptable.W" not in O.param_shapes(cfg1)
+    p1 = O.init_params(cfg1, seed=3, weights_std=0.4)
+    p2 = OrderedDict(p1)
+    p2["/recognizer/generator/readout/lookupfeedback/lookuptable.W"] = np.eye(6)
+    x, m, labels, lm = O.synthetic_batch(cfg1, B=3, T=12, seed=2, label_div=3)
+    assert_allclose(O.recognizer_cost(cfg1, p1, x, m, labels, lm), O.recognizer_cost(cfg2, p2, x, m, labels, lm), rtol=1e-12)
