@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   float* w3s = smem + off; off += (size_t)C * ws3;
   float* loc = smem + off; off += (size_t)3 * DS_ROWS * a.nc2;
   off = (off + 3) & ~(size_t)3;
-  float* red = smem + off;
+  // the cross-warp scratch of the dense tiles may live in the attention phase's reduction scratch: a CTA runs its
+  // phases one after the other (CTA barriers in between), so the two never hold live data at the same time
+  float* red = a.red_alias ? att_carve(att, M, E, a.K, a.n, a.tc_cap, cs).sred : smem + off;
 
   // ---- one-time staging: weight slices + attention constants -----------------------------
   for (int i = tid; i < (E + C) * a.nc1; i += DS_THREADS) {
@@ -444,7 +446,9 @@ size_t derive(DecScanArgs& a, int cs, int G, bool want_islands) {
   f += (size_t)(E + C) * (a.nc1 + 4) + (size_t)C * (a.nc2 + 4) + (size_t)C * (a.nc3 + 4);
   f = (f + 3) & ~(size_t)3;
   f += (size_t)3 * DS_ROWS * a.nc2 + 4;
-  f += (size_t)DS_WARPS * DS_ROWS * std::max(a.nc1, std::max(a.nc2, a.nc3));
+  const size_t red_f = (size_t)DS_WARPS * DS_ROWS * std::max(a.nc1, std::max(a.nc2, a.nc3));
+  a.red_alias = att_red_floats(E, a.tc_cap) >= red_f ? 1 : 0;
+  if (!a.red_alias) f += red_f;
   const size_t bytes = f * sizeof(float) + 64;
   return bytes <= 227 * 1024 ? bytes : 0;
 }

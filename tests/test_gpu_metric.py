@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import bench
-from helpers import O, PYRAMID, make_recognizer, rel_err
+from helpers import O, PYRAMID, make_recognizer, package, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -98,3 +98,30 @@ def test_smoke_passes_with_decoder_postcondition(monkeypatch):
     monkeypatch.setenv("LVSR_DEC_CHECK", "1")
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_long_utterance_persistent_decoder_matches_oracle(monkeypatch):
+    """16 rows x T' = 1600 (the shape class of BASELINE config 5): 4-CTA clusters with 400-position chunks; the dense
+    tiles' scratch shares the attention scratch so that the persistent kernel fits in shared memory."""
+    _torch()
+    monkeypatch.setenv("LVSR_DEC_CHECK", "1")
+    net = dict(num_features=40, dims_bidir=[128], subsample=[1], dim_dec=128, dim_matcher=256, conv_n=50,
+               conv_num_filters=10, num_phonemes=32, post_merge_dims=[128], maxout_pieces=2)
+    cfg = O.make_config(prior=dict(type="window_around_median", before=60, after=60), **net)
+    params = O.init_params(cfg, seed=8, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=16, T=1600, seed=3, label_div=100)
+    att, attm = O.encoder(cfg, params, x, m)
+    want = O.cost_matrix(cfg, params, att, attm, labels, lm, return_all=True)
+    rec = make_recognizer(cfg, params)
+    import ctypes as C
+    pkg = package()
+    lib = pkg._lib.load()
+    lib.lvsr_profile_enable(1)
+    got = rec.cost_matrix(labels, lm, att.astype(np.float32), attm.astype(np.float32), return_all=True)
+    tot, cnt = C.c_double(), C.c_int64()
+    lib.lvsr_profile_read(b"attention", C.byref(tot), C.byref(cnt))
+    lib.lvsr_profile_enable(0)
+    assert cnt.value == 0, "the step-wise fallback ran instead of the persistent decoder"
+    assert rec.launch_status() == (0, 0)
+    for k in ("costs", "weights", "energies", "states", "weighted_averages"):
+        assert rel_err(got[k].cpu().numpy(), want[k]) < TOL, k
