@@ -196,3 +196,35 @@ def test_one_of_n_feedback_cost_and_gradients():
     want = O.recognizer_cost(cfg, params, *batch)
     got = rec.cost(*batch)
     assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_wsj_training_batch_matches_golden_gradients():
+    """WSJ architecture, B = 16 (island-mode persistent decoder), T*B = 5120 rows (tcgen05 backward GEMMs), against the
+    committed float64 gradient oracle (tests/golden/make_train_golden.py): per parameter sum, sum |.|, max |.| and a random
+    projection of the gradient."""
+    _torch()
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_golden.npz"))
+    cfg = O.make_config(**WSJ)
+    params = O.init_params(cfg, seed=1, scale=10.0)
+    batch = O.synthetic_batch(cfg, B=16, T=320, seed=17)
+    pkg = package()
+    rec = make_recognizer(cfg, params)
+    algo = pkg.GradientDescent(recognizer=rec, step_rule=pkg.CompositeRule([pkg.RemoveNotFinite(0.0)]))
+    cost, grads = algo.cost_and_gradients(dict(zip(algo.SOURCES, batch)))
+    assert abs(cost - float(gold["cost"])) <= 1e-4 * abs(float(gold["cost"]))
+    names, stats = [str(n) for n in gold["names"]], gold["stats"]
+    assert names == list(grads)
+    rng = np.random.RandomState(7)
+    gmax = stats[:, 2].max()
+    worst = 0.0
+    for k, want in zip(names, stats):
+        g = grads[k].astype(np.float64)
+        r = rng.normal(size=g.shape)
+        got = np.array([g.sum(), np.abs(g).sum(), np.abs(g).max(), (g * r).sum()])
+        # sums of n entries of size <= max|g| carry rounding of order sqrt(n) * eps * max|g|; 1e-4 of the natural scale of each statistic
+        scale = np.array([want[1], want[1], want[2], want[2] * np.sqrt(g.size)]) + 1e-6 * gmax
+        err = np.abs(got - want) / scale
+        worst = max(worst, err.max())
+        assert (err < 2e-4).all(), (k, err)
+    print("worst relative error over %d parameters: %.2e" % (len(names), worst))
