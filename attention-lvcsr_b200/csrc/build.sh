@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJS=()
 for f in gemm gemm_tc bigru bigru_bwd attention decoder dec_scan train api; do
   stale=0
-  for h in kernels.h common.cuh attention_row.cuh model.h ../../include/lvsr_b200.h; do
+  for h in kernels.h common.cuh attention_row.cuh model.h train_kernels.cuh ../../include/lvsr_b200.h; do
     if [ "$h" -nt "$f.o" ]; then stale=1; fi
   done
   if [ ! -f "$f.o" ] || [ "$f.cu" -nt "$f.o" ] || [ $stale = 1 ]; then

@@ -228,3 +228,23 @@ def test_wsj_training_batch_matches_golden_gradients():
         worst = max(worst, err.max())
         assert (err < 2e-4).all(), (k, err)
     print("worst relative error over %d parameters: %.2e" % (len(names), worst))
+
+
+def test_single_utterance_single_label_and_determinism():
+    """Edge shapes (B = 1, L = 2) and run-to-run determinism: every reduction of the backward pass has a fixed order
+    (split-K partials, per-CTA partial sums, no floating-point atomics), so two calls give bit-identical gradients."""
+    _torch()
+    cfg = O.make_config(**PYRAMID)
+    params = O.init_params(cfg, seed=5, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=1, T=24, seed=2, label_div=24)
+    assert labels.shape[0] == 2
+    algo, rec = _check_grads(cfg, params, (x, m, labels, lm))
+    batch = O.synthetic_batch(cfg, B=32, T=64, seed=3)            # tensor-core split-K path
+    pkg = package()
+    rec2 = make_recognizer(cfg, params)
+    algo2 = pkg.GradientDescent(recognizer=rec2, step_rule=pkg.CompositeRule([pkg.RemoveNotFinite(0.0)]))
+    c1, g1 = algo2.cost_and_gradients(dict(zip(algo2.SOURCES, batch)))
+    c2, g2 = algo2.cost_and_gradients(dict(zip(algo2.SOURCES, batch)))
+    assert c1 == c2
+    for k in g1:
+        assert np.array_equal(g1[k], g2[k]), k
