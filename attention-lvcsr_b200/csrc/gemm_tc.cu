@@ -26,12 +26,19 @@ namespace lvsr {
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;
-constexpr int TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;      // TC_BN: the granularity N must be a multiple of
 constexpr int TC_THREADS = 192;
-constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * sizeof(float);          // 16 KB
-constexpr uint32_t TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                      // A_hi, A_lo, B_hi, B_lo
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_BK * sizeof(float);          // 16 KB: one 128-row operand tile
+// Two tile shapes: 128 x 128 (3 stages) and 128 x 256 (2 stages).  The wide tile moves 25 % fewer operand bytes per
+// MAC -- the kernel is bound by L2 -> SM operand traffic (every value is a hi AND a lo fp32), not by the tensor pipe.
+template <int BN> struct TcShape {
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr uint32_t B_TILE_BYTES = (uint32_t)BN * TC_BK * sizeof(float);
+  static constexpr uint32_t STAGE_BYTES = 2 * TC_TILE_BYTES + 2 * B_TILE_BYTES;            // A_hi, A_lo, B_hi, B_lo
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = BN
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -87,9 +94,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                              ((uint32_t)(TC_BM >> 4) << 24);
 
 struct TcGemmParams {
   float* C;
@@ -99,6 +103,7 @@ struct TcGemmParams {
   long long c_split_stride;    // elements between the partial outputs of consecutive splits
 };
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -106,12 +111,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned tiles
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TC_STAGES = TcShape<BN>::STAGES;
+  constexpr uint32_t TC_STAGE_BYTES = TcShape<BN>::STAGE_BYTES, B_TILE = TcShape<BN>::B_TILE_BYTES;
+  constexpr uint32_t TC_IDESC = TcShape<BN>::IDESC;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(tiles + (size_t)TC_STAGES * TC_STAGE_BYTES);
   // bars[0..S): full, bars[S..2S): empty, bars[2S]: accumulator ready; then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, p.K / TC_BK - kb0);
   p.C += (long long)blockIdx.z * p.c_split_stride;
@@ -126,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_addr(tmem_slot)),
-                 "r"((uint32_t)TC_BN)
+                 "r"((uint32_t)BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -148,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tma_load_2d(base + 0 * TC_TILE_BYTES, &map_a_hi, (kb0 + kb) * TC_BK, m0, full);
         tma_load_2d(base + 1 * TC_TILE_BYTES, &map_a_lo, (kb0 + kb) * TC_BK, m0, full);
         tma_load_2d(base + 2 * TC_TILE_BYTES, &map_b_hi, (kb0 + kb) * TC_BK, n0, full);
-        tma_load_2d(base + 3 * TC_TILE_BYTES, &map_b_lo, (kb0 + kb) * TC_BK, n0, full);
+        tma_load_2d(base + 2 * TC_TILE_BYTES + B_TILE, &map_b_lo, (kb0 + kb) * TC_BK, n0, full);
       }
     }
   } else if (warp == 1) {
@@ -161,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tc_fence_after();
         const uint32_t base = smem_addr(tiles + (size_t)s * TC_STAGE_BYTES);
         const uint64_t da_hi = make_smem_desc(base + 0 * TC_TILE_BYTES), da_lo = make_smem_desc(base + 1 * TC_TILE_BYTES);
-        const uint64_t db_hi = make_smem_desc(base + 2 * TC_TILE_BYTES), db_lo = make_smem_desc(base + 3 * TC_TILE_BYTES);
+        const uint64_t db_hi = make_smem_desc(base + 2 * TC_TILE_BYTES), db_lo = make_smem_desc(base + 2 * TC_TILE_BYTES + B_TILE);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {           // UMMA K = 8 for tf32 = 32 bytes = +2 in 16-byte units
           const uint64_t adv = (uint64_t)(k * 2);
@@ -180,7 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int q = warp & 3;                              // TMEM lane quarter this warp may touch
     const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < TC_BN; c += 32) {
+    for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
       asm volatile(
@@ -212,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
   }
 }
 
@@ -290,10 +298,10 @@ int get_encode() {
 }
 
 // 2-D fp32 tensor [rows, K] (K contiguous), box = [128 rows, 32 floats], 128-byte swizzle
-int make_map(CUtensorMap* map, const float* ptr, long long rows, int K) {
+int make_map(CUtensorMap* map, const float* ptr, long long rows, int K, int box_rows = TC_BM) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -352,15 +360,18 @@ int gemm_tc_presplit(const float* A_hi, const float* A_lo, int M, const float* B
   ProfScope prof("gemm", stream);
   LVSR_CHECK(M >= 1 && N % TC_BN == 0 && Kpad % TC_BK == 0 && Kpad >= TC_BK && splits >= 1, "gemm_tc_presplit: unsupported shape M=%d N=%d K=%d", M, N, Kpad);
   if (int rc = get_encode()) return rc;
+  const bool wide = (N % 256 == 0) && getenv("LVSR_TC_NARROW") == nullptr;
+  const int BN = wide ? 256 : 128;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int rc = make_map(&ma_hi, A_hi, M, Kpad)) return rc;
   if (int rc = make_map(&ma_lo, A_lo, M, Kpad)) return rc;
-  if (int rc = make_map(&mb_hi, B_hi, N, Kpad)) return rc;
-  if (int rc = make_map(&mb_lo, B_lo, N, Kpad)) return rc;
+  if (int rc = make_map(&mb_hi, B_hi, N, Kpad, BN)) return rc;
+  if (int rc = make_map(&mb_lo, B_lo, N, Kpad, BN)) return rc;
   static bool configured[LVSR_MAX_DEVICES] = {false};
   const int dev = current_device();
   if (!configured[dev]) {
-    LVSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    LVSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<128>::SMEM));
+    LVSR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcShape<256>::SMEM));
     configured[dev] = true;
   }
   const int total_kb = Kpad / TC_BK;
@@ -369,8 +380,9 @@ int gemm_tc_presplit(const float* A_hi, const float* A_lo, int M, const float* B
   p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = Kpad; p.ldc = ldc;
   p.kb_per_split = ceil_div(total_kb, splits);
   p.c_split_stride = split_stride;
-  dim3 grid(N / TC_BN, ceil_div(M, TC_BM), ceil_div(total_kb, p.kb_per_split));
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  dim3 grid(N / BN, ceil_div(M, TC_BM), ceil_div(total_kb, p.kb_per_split));
+  if (wide) gemm_tc_kernel<256><<<grid, TC_THREADS, TcShape<256>::SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else gemm_tc_kernel<128><<<grid, TC_THREADS, TcShape<128>::SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   LVSR_LAUNCH_CHECK();
   return 0;
 }

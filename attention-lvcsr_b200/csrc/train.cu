@@ -116,7 +116,7 @@ int make_tc_operand(Arena& ws, const float* src, int R, int cols, int ld, TcOper
 int gemm_tn_tc(Arena& ws, const TcOperand& A, int a0, int Mo, const TcOperand& B, int b0, int N, float* C, int ldc,
                bool accumulate, cudaStream_t st) {
   ProfScope prof("gemm_tn", st);
-  const int tiles = ceil_div(Mo, 128) * (N / 128);
+  const int tiles = ceil_div(Mo, 128) * (N / (N % 256 == 0 ? 256 : 128));
   const int want = std::max(1, std::min(32, ceil_div(device_sm_count(), tiles)));
   const int splits = gemm_tc_splits_launched(A.Kpad, want);
   const size_t mark = ws.off;
