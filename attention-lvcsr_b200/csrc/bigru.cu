@@ -16,12 +16,15 @@
 //     registers straight into the receiver's shared memory and credit the RECEIVER's mbarrier
 //     (complete_tx); no staging buffer, no proxy fence, no CTA or cluster barrier in the loop --
 //     a warp only ever waits for "all RB*D*4 bytes of h (or h*r) have landed".  h never leaves the chip.
-//   * inside a warp k is split over 8 lanes and the columns over the other 4 (see the kernel);
+//   * inside a warp k is split over 16 lanes and the warp's columns over the other 2 (see the kernel);
 //     everything the epilogues need from other lanes travels by shuffle.
 //   * the fork pre-activations of step t+1 are prefetched into registers during step t.
-// History (profiles/): r1a 4-byte remote stores + barrier.cluster (30 % of the kernel in the fence,
-// 8.6 us/step) -> bulk DSMEM copies + mbarrier (3.07 us) -> this layout (2.76 us; the kernel is bound
-// by the SM's issue slots at ~50 % utilisation: 714 instructions per warp and step, 386 of them FFMA).
+//   * TAPE (training): the gates / candidate overwrite the pre-activations they were computed from and every
+//     frame of h is kept (hext), for the reverse-time scan of bigru_bwd.cu; compiled out of the inference kernel.
+// History (profiles/): r1a 4-byte remote stores + barrier.cluster (30 % of the kernel in the fence, 8.6 us/step)
+// -> bulk DSMEM copies + mbarrier (3.07 us) -> k over 8 lanes, FFMA2 (2.76 us) -> k over 16 lanes, 4 CTAs x 16 warps,
+// st.async from registers (2.34 us in the loop, 2.67 us/step with launch and staging): the products are bound by the
+// shared-memory return path of the h loads, the rest is lock-step latency (profiles/r1g_summary.md).
 #include "kernels.h"
 
 namespace lvsr {
