@@ -81,6 +81,11 @@ SIGNATURES = {
     "lvsr_search_expand": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lvsr_search_advance": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I,
                                       _P, _P, _P, _P, _P, _P]),
+    "lvsr_beam_search_many": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, C.c_double, C.c_double, _I, C.POINTER(_P), _P]),
+    "lvsr_search_result_count": (C.c_int, [_P, _I]),
+    "lvsr_search_result_length": (C.c_int, [_P, _I, _I]),
+    "lvsr_search_result_get": (C.c_int, [_P, _I, _I, _P, _P]),
+    "lvsr_search_result_destroy": (C.c_int, [_P]),
     "lvsr_recognizer_cost_host": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "lvsr_train_cost_and_grads": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, _P, _P, _P]),
     "lvsr_train_apply_updates": (C.c_int, [_P, _P, C.c_float, C.POINTER(LvsrTrainConfig), _P]),

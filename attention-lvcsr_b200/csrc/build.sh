@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include -I."
 OBJS=()
-for f in gemm gemm_tc bigru bigru_bwd attention decoder dec_scan train api; do
+for f in gemm gemm_tc bigru bigru_bwd attention decoder dec_scan train search api; do
   stale=0
   for h in kernels.h common.cuh attention_row.cuh model.h train_kernels.cuh ../../include/lvsr_b200.h; do
     if [ "$h" -nt "$f.o" ]; then stale=1; fi

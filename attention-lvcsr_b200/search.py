@@ -117,6 +117,10 @@ class BeamSearch(object):
         P = r.preprocess(att)
         Tp = int(att.shape[0])
         enc_len = np.asarray([r.encoded_length(t) for t in lens], dtype=np.int32)
+        if validate_solution_function is None and not getattr(self, "force_python_loop", False):
+            done_lists = self._search_many_native(att, P, attm, Tp, U, enc_len, max_lengths, eol_symbol, ignore_first_eol,
+                                                  char_discount, round_to_inf, stop_on)
+            return self._format_results(done_lists, as_arrays, raise_on_failure)
         reuse = 1 if r.net["prior"].get("type", "expanding") == "expanding" else 0
         st = r._initial_states(Tp, U)
         states, weights, step = st["states"], st["weights"], st["step"]
@@ -248,15 +252,45 @@ class BeamSearch(object):
             else:
                 states, weights, step = n_states, n_w, n_step
 
+        return self._format_results([sorted(utts[u]["done"], key=discounted) for u in range(U)], as_arrays, raise_on_failure)
+
+    def _search_many_native(self, att, P, attm, Tp, U, enc_len, max_lengths, eol_symbol, ignore_first_eol,
+                            char_discount, round_to_inf, stop_on):
+        """The loop in C++ (lvsr_beam_search_many): per utterance the ranked `done` list of (tokens, costs) histories."""
+        import ctypes as C
+        r = self.recognizer
+        lib, h = _lib.load(), r._require_ready()
+        lens = np.ascontiguousarray(enc_len, dtype=np.int32)
+        maxl = np.ascontiguousarray([int(m) for m in max_lengths], dtype=np.int32)
+        res = C.c_void_p()
+        _lib.check(lib.lvsr_beam_search_many(
+            h, att.data_ptr(), P.data_ptr(), attm.data_ptr(), Tp, U, lens.ctypes.data, maxl.ctypes.data, int(self.beam_size),
+            int(eol_symbol), int(bool(ignore_first_eol)), float(char_discount or 0), float(round_to_inf),
+            1 if stop_on == "optimistic_future_cost" else 0, C.byref(res), r._stream()))
+        out = []
+        try:
+            for u in range(U):
+                done = []
+                for j in range(lib.lvsr_search_result_count(res, u)):
+                    n = lib.lvsr_search_result_length(res, u, j)
+                    tok = np.empty((n,), dtype=np.int64)
+                    cst = np.empty((n,), dtype=np.float32)
+                    _lib.check(lib.lvsr_search_result_get(res, u, j, tok.ctypes.data, cst.ctypes.data))
+                    done.append((tok, cst))
+                out.append(done)
+        finally:
+            lib.lvsr_search_result_destroy(res)
+        return out
+
+    def _format_results(self, done_lists, as_arrays, raise_on_failure):
+        """result_to_lists / the array form of B/search.py:384-407 from ranked `done` lists."""
         results = []
-        for u in range(U):
-            done = utts[u]["done"]
+        for done in done_lists:
             if not done:
                 if raise_on_failure:
                     raise CandidateNotFoundError()
                 results.append(None)
                 continue
-            done = sorted(done, key=discounted)
             max_len = max(seq.shape[0] for seq, _ in done)
             all_outputs = np.zeros((max_len, len(done)))
             all_masks = np.zeros((max_len, len(done)))

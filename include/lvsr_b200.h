@@ -171,6 +171,25 @@ int lvsr_search_advance(lvsr_model* m, const float* attended_dev, const float* p
                         float* next_states_dev, float* next_wavg_dev, float* next_weights_dev,
                         float* next_energies_dev, int64_t* next_step_dev, void* stream);
 
+/* The whole search loop of BeamSearch.search (libs/blocks/blocks/search.py:244-399) for U utterances decoded in
+ * lock-step: the reference's bookkeeping (histories, `done`, both stopping criteria, final ranking) in C++ around
+ * lvsr_search_expand / lvsr_search_advance; per step one small H2D, one small D2H, one synchronisation for ALL
+ * utterances.  utt_len_host[u] = valid encoded frames, max_length_host[u] = int(T_u / max_decoded_length_scale)
+ * (lvsr/bricks/recognizer.py:519-520).  stop_on_optimistic: 0 = 'patience', 1 = 'optimistic_future_cost'.
+ * Result: per utterance the finished hypotheses ranked by cost - char_discount * length, each as its full token
+ * and cumulative-cost history INCLUDING the initial symbol (what BeamSearch keeps in `done`).  A
+ * validate_solution_function callback is not available here (the Python mirror runs its own loop for that). */
+typedef struct lvsr_search_result lvsr_search_result;
+int lvsr_beam_search_many(lvsr_model* m, const float* attended_dev, const float* preprocessed_dev,
+                          const float* attended_mask_dev, int32_t Tp, int32_t U, const int32_t* utt_len_host,
+                          const int32_t* max_length_host, int32_t beam_size, int32_t eol_symbol,
+                          int32_t ignore_first_eol, double char_discount, double round_to_inf,
+                          int32_t stop_on_optimistic, lvsr_search_result** result, void* stream);
+int lvsr_search_result_count(const lvsr_search_result* r, int32_t utt);                     /* finished hypotheses */
+int lvsr_search_result_length(const lvsr_search_result* r, int32_t utt, int32_t j);         /* history length     */
+int lvsr_search_result_get(const lvsr_search_result* r, int32_t utt, int32_t j, int64_t* tokens, float* costs);
+int lvsr_search_result_destroy(lvsr_search_result* r);
+
 /* ---- host-buffer entry points (the call a user of the reference makes) -------------
  * SpeechRecognizer.cost on a batch (lvsr/bricks/recognizer.py:375-390): H2D copies,
  * encoder, cost_matrix, D2H of costs [L,B]; synchronises.  Buffers should be pinned. */

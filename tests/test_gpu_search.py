@@ -83,3 +83,39 @@ def test_search_launch_count_is_shared_by_all_utterances():
     many = lib.lvsr_launch_count(1)
     print("launches: 1 utterance", one, "12 utterances", many)
     assert many <= 1.5 * one                              # not 12x
+
+
+@pytest.mark.parametrize("stop_on,char_discount", [("patience", 0.0), ("optimistic_future_cost", 0.2)])
+def test_native_loop_equals_python_loop(stop_on, char_discount):
+    """lvsr_beam_search_many (the loop in C++) returns exactly what the Python mirror of BeamSearch.search returns:
+    every finished hypothesis, its per-step costs and the ranking."""
+    _torch()
+    cfg = O.make_config(prior=dict(type="window_around_mean", before=7, after=7), max_decoded_length_scale=2.5, **PYRAMID)
+    params = _peaky(cfg, 4)
+    rng = np.random.RandomState(8)
+    utts = [rng.normal(size=(T, cfg["num_features"])).astype(np.float32) for T in (60, 33, 48, 25, 57)]
+    rec = make_recognizer(cfg, params)
+    rec.init_beam_search(6)
+    bs = rec._beam_search
+    maxl = [int(u.shape[0] / 2.5) for u in utts]
+    native = bs.search_many(utts, cfg["eos_label"], maxl, stop_on=stop_on, char_discount=char_discount,
+                            raise_on_failure=False, as_arrays=True)
+    bs.force_python_loop = True
+    python = bs.search_many(utts, cfg["eos_label"], maxl, stop_on=stop_on, char_discount=char_discount,
+                            raise_on_failure=False, as_arrays=True)
+    bs.force_python_loop = False
+    assert len(native) == len(python) == 5
+    compared = 0
+    for a, b in zip(native, python):
+        assert (a is None) == (b is None)
+        if a is None:
+            continue
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y)
+        compared += a[0].shape[1]
+    assert compared >= 1
+    # a validate_solution_function routes through the Python loop and filters hypotheses
+    only_short = bs.search_many(utts[:1], cfg["eos_label"], maxl[:1], stop_on=stop_on, char_discount=char_discount,
+                                raise_on_failure=False, validate_solution_function=lambda inputs, seq: len(seq) <= 3)
+    if only_short[0] is not None:
+        assert all(len(o) <= 2 for o in only_short[0][0])
