@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblvsr_b200.so")
+# LVSR_B200_LIB: load another build of the same library (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("LVSR_B200_LIB") or os.path.join(_HERE, "csrc", "liblvsr_b200.so")
 
 LVSR_MAX_LAYERS = 8
 NORMALIZERS = {"softmax": 0, "logistic": 1, "relu": 2}

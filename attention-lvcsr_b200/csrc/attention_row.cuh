@@ -38,11 +38,13 @@ __host__ __device__ inline size_t att_red_floats(int E, int tc_cap) {
 }
 
 // Shared-memory footprint (floats) of attention_row for a chunk capacity of tc_cap positions.
-__host__ __device__ inline size_t att_smem_floats(int M, int E, int K, int n, int tc_cap, int cs) {
+// wh_rows: rows of the handler copy in shared memory: 16 (zero-padded to the MMA depth, unpredicated fragment loads: the
+// fast default) or K (compact; the planner falls back to it when the padded copy does not fit, e.g. 16 rows x T' = 2000)
+__host__ __device__ inline size_t att_smem_floats(int M, int E, int K, int n, int tc_cap, int cs, int wh_rows = 16) {
   size_t f = 0;
   f += M;                                         // sq
   f += M;                                         // sv
-  f += (size_t)16 * M;                            // sWh (rows >= K are zero)
+  f += (size_t)wh_rows * M;                       // sWh (rows >= K are zero, or supplied by predicates in the compact layout)
   f += (size_t)(2 * n + 1) * att_filter_row(K);   // sfiltT [tap][filter]
   f += tc_cap + 2 * n + 8;                        // salpha
   f += (size_t)(tc_cap + 16) * 16;                // sF: packed bf16 pairs, 8 hi + 8 lo words per position
@@ -70,6 +72,7 @@ struct AttRowIO {
   float* ctx_out;        // [E]
   int u;                 // utterance column of this row in P/H/maskH
   int U, Tp, M, E, K, n, normalizer;
+  int wh_rows = 16;      // handler rows held in shared memory (att_smem_floats)
   int b0, b1;            // global window cut
   float lo, hi;          // strict per-row bounds (additional mask)
   // optional: position statistic of the NEW alignment for the next step's window prior
@@ -110,12 +113,12 @@ struct AttSmem {
   uint32_t* sF;          // [(tc_cap+16)][16]: words 0..7 = hi pairs, 8..15 = lo pairs
 };
 
-__device__ __forceinline__ AttSmem att_carve(float* smem, int M, int E, int K, int n, int tc_cap, int cs) {
+__device__ __forceinline__ AttSmem att_carve(float* smem, int M, int E, int K, int n, int tc_cap, int cs, int wh_rows = 16) {
   AttSmem s;
   float* p = smem;
   s.sq = p; p += M;
   s.sv = p; p += M;
-  s.sWh = p; p += (size_t)16 * M;
+  s.sWh = p; p += (size_t)wh_rows * M;
   s.sfiltT = p; p += (size_t)(2 * n + 1) * att_filter_row(K);
   p += (4 - ((p - smem) & 3)) & 3;
   s.salpha = p; p += tc_cap + 2 * n + 8;
@@ -134,10 +137,10 @@ __device__ __forceinline__ AttSmem att_carve(float* smem, int M, int E, int K, i
 // Constants that never change during a sequence: energy vector, handler (zero-padded to 16
 // rows), transposed + zero-padded filter bank.  Persistent callers stage them once.
 __device__ __forceinline__ void att_stage_constants(const AttSmem& s, const float* v, const float* Wh,
-                                                    const float* filt, int M, int K, int n) {
+                                                    const float* filt, int M, int K, int n, int wh_rows = 16) {
   const int tid = threadIdx.x, w = 2 * n + 1, fw = att_filter_row(K);
   for (int i = tid; i < M; i += ATT_NT) s.sv[i] = v[i];
-  for (int i = tid; i < 16 * M; i += ATT_NT) s.sWh[i] = (i / M < K) ? Wh[i] : 0.f;
+  for (int i = tid; i < wh_rows * M; i += ATT_NT) s.sWh[i] = (i / M < K) ? Wh[i] : 0.f;
   for (int i = tid; i < w * fw; i += ATT_NT) {
     const int j = i / fw, k = i % fw;
     s.sfiltT[i] = (k < K) ? filt[(size_t)k * w + j] : 0.f;
@@ -158,7 +161,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 // NTW: 8-column tiles of the matcher dimension per warp (M = 128 * NTW).
-template <int NTW>
+template <int NTW, bool COMPACT>
 __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s, int nt, int t0, int tc_cap) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tig = lane & 3;
@@ -170,8 +173,9 @@ __device__ __forceinline__ void att_energies(const AttRowIO& a, const AttSmem& s
   for (int j = 0; j < NTW; ++j) {
     const int n0 = (warp * NTW + j) * 8;
     const int colb = n0 + g;                       // B fragment column
-    const float w00 = s.sWh[(size_t)(2 * tig) * M + colb], w01 = s.sWh[(size_t)(2 * tig + 1) * M + colb];
-    const float w10 = s.sWh[(size_t)(2 * tig + 8) * M + colb], w11 = s.sWh[(size_t)(2 * tig + 9) * M + colb];
+    // B fragment rows 2tig, 2tig+1, 2tig+8, 2tig+9 of the 16-deep product; only K rows exist (K <= 16)
+    auto wh = [&](int row) -> float { return (!COMPACT || row < a.K) ? s.sWh[(size_t)row * M + colb] : 0.f; };
+    const float w00 = wh(2 * tig), w01 = wh(2 * tig + 1), w10 = wh(2 * tig + 8), w11 = wh(2 * tig + 9);
     const float h00 = bf16_round(w00), h01 = bf16_round(w01), h10 = bf16_round(w10), h11 = bf16_round(w11);
     bh[j][0] = pack_bf16(h00, h01);
     bh[j][1] = pack_bf16(h10, h11);
@@ -243,6 +247,7 @@ __device__ __forceinline__ float gmax_of(const float* xs, int cs) {
 // sentinel-initialised buffers (common.cuh, "the data is the flag"): they are read with polling
 // loads and the outputs other CTAs consume are written with gpu-scope stores.
 // `entry_wait_pending`: the caller issued barrier.cluster.arrive at kernel entry.
+template <bool COMPACT = false>
 __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, int tc_cap, int rank, int cs,
                                               bool constants_staged, bool flow,
                                               bool entry_wait_pending) {
@@ -250,7 +255,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = ATT_NT, NW = ATT_NW;
   const int M = a.M, E = a.E, K = a.K, n = a.n, w = 2 * n + 1, Tp = a.Tp, U = a.U, u = a.u;
-  const AttSmem s = att_carve(smem, M, E, K, n, tc_cap, cs);
+  const AttSmem s = att_carve(smem, M, E, K, n, tc_cap, cs, a.wh_rows);
 
   const int b0 = a.b0;
   const int Tw = max(0, a.b1 - a.b0);
@@ -260,7 +265,7 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
 
   ATT_STAMP(0);
   // ---- stage the row's query, the slice of the previous alignment, zero the energies ----
-  if (!constants_staged) att_stage_constants(s, a.v, a.Wh, a.filt, M, K, n);
+  if (!constants_staged) att_stage_constants(s, a.v, a.Wh, a.filt, M, K, n, a.wh_rows);
   {
     const int len = nt + 2 * n + 8;
     for (int i = tid; i < len; i += NT) {
@@ -349,9 +354,9 @@ __device__ __forceinline__ void attention_row(const AttRowIO& a, float* smem, in
   ATT_STAMP(2);
 
   // ---- energies: e[t] = v . tanh(P[t] + q + F[t] . Wh) on the tensor cores -------------
-  if (M == 512) att_energies<4>(a, s, nt, t0, tc_cap);
-  else if (M == 256) att_energies<2>(a, s, nt, t0, tc_cap);
-  else att_energies<1>(a, s, nt, t0, tc_cap);
+  if (M == 512) att_energies<4, COMPACT>(a, s, nt, t0, tc_cap);
+  else if (M == 256) att_energies<2, COMPACT>(a, s, nt, t0, tc_cap);
+  else att_energies<1, COMPACT>(a, s, nt, t0, tc_cap);
   __syncthreads();
   {
     // e[t] = the 16 warps' partial sums, added in a fixed order

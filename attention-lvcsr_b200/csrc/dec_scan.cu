@@ -203,6 +203,9 @@ __device__ __forceinline__ void dense_dispatch(int nq, const DenseIO& d, const f
   __trap();   // plan() only admits the shapes above
 }
 
+// COMPACT: the handler copy in shared memory holds only its K rows (a.wh_rows == K); a separate instantiation so that
+// the default kernel's energy loop stays exactly the unpredicated code (it is sensitive to every extra register)
+template <bool COMPACT>
 __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
 
   // ---- shared memory: [attention region][w1][w2][w3][red] -----------------------------
   float* att = smem;
-  size_t off = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
+  size_t off = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs, a.wh_rows);
   off = (off + 3) & ~(size_t)3;
   const int ws1 = a.nc1 + 4, ws2 = a.nc2 + 4, ws3 = a.nc3 + 4;
   float* w1s = smem + off; off += (size_t)(E + C) * ws1;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
   off = (off + 3) & ~(size_t)3;
   // the cross-warp scratch of the dense tiles may live in the attention phase's reduction scratch: a CTA runs its
   // phases one after the other (CTA barriers in between), so the two never hold live data at the same time
-  float* red = a.red_alias ? att_carve(att, M, E, a.K, a.n, a.tc_cap, cs).sred : smem + off;
+  float* red = a.red_alias ? att_carve(att, M, E, a.K, a.n, a.tc_cap, cs, a.wh_rows).sred : smem + off;
 
   // ---- one-time staging: weight slices + attention constants -----------------------------
   for (int i = tid; i < (E + C) * a.nc1; i += DS_THREADS) {
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
     const int k = i / a.nc3, c = i % a.nc3, col = cgi * a.nc3 + c;
     w3s[(size_t)k * ws3 + c] = (in3 && col < M) ? a.Ws[(long long)k * M + col] : 0.f;
   }
-  att_stage_constants(att_carve(att, M, E, a.K, a.n, a.tc_cap, cs), a.v, a.Wh, a.filt, M, a.K, a.n);
+  att_stage_constants(att_carve(att, M, E, a.K, a.n, a.tc_cap, cs, a.wh_rows), a.v, a.Wh, a.filt, M, a.K, a.n, a.wh_rows);
   __syncthreads();
 
   // query of the first step: q = s_0 . W_state
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
         b1 = (int)ceil(ee);
       } else {
         // the batch-global cut needs the position statistic of EVERY row of the previous step
-        float* wsh = att + att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs) - 8;   // spare floats at the tail
+        float* wsh = att + att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs, a.wh_rows) - 8;   // spare floats at the tail
         if (warp == 0) {
           float mn = 1e30f, mx = -1e30f;
           for (int r = lane; r < R; r += 32) {
@@ -364,11 +367,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) dec_scan_kernel(DecScanArgs a) 
       io.ctx_out = ctx_cur + (long long)row * E;
       io.u = row; io.U = R; io.Tp = a.Tp; io.M = M; io.E = E; io.K = a.K; io.n = a.n;
       io.normalizer = a.normalizer;
+      io.wh_rows = a.wh_rows;
       io.b0 = b0; io.b1 = b1; io.lo = lo; io.hi = hi;
       io.rowpos_out = (a.prior.type == LVSR_PRIOR_EXPANDING) ? nullptr : (rowpos_wr + row);
       io.rowpos_mode = a.prior.type;
       io.trace = (a.trace && bid == 0) ? a.trace + (size_t)2 * a.L * 9 + (size_t)i * 8 : nullptr;
-      attention_row(io, att, a.tc_cap, rank, cs, true, true, false);
+      attention_row<COMPACT>(io, att, a.tc_cap, rank, cs, true, true, false);
     }
     DS_STAMP(1);
     if (a.trace && rank == 0 && tid == 0 && cluster_id < R)
@@ -441,16 +445,21 @@ size_t derive(DecScanArgs& a, int cs, int G, bool want_islands) {
   a.nc1 = 3 * a.nc2;
   a.nc3 = round_up8(ceil_div(M, a.ncg));
   if (a.nc1 > 24 || a.nc2 > 24 || a.nc3 > 24) return 0;
-  size_t f = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs);
-  f = (f + 3) & ~(size_t)3;
-  f += (size_t)(E + C) * (a.nc1 + 4) + (size_t)C * (a.nc2 + 4) + (size_t)C * (a.nc3 + 4);
-  f = (f + 3) & ~(size_t)3;
-  f += (size_t)3 * DS_ROWS * a.nc2 + 4;
   const size_t red_f = (size_t)DS_WARPS * DS_ROWS * std::max(a.nc1, std::max(a.nc2, a.nc3));
   a.red_alias = att_red_floats(E, a.tc_cap) >= red_f ? 1 : 0;
-  if (!a.red_alias) f += red_f;
-  const size_t bytes = f * sizeof(float) + 64;
-  return bytes <= 227 * 1024 ? bytes : 0;
+  // handler copy: zero-padded to 16 rows (fast path) if it fits, else only its K rows (long utterances)
+  for (int rows : {16, a.K}) {
+    a.wh_rows = rows;
+    size_t f = att_smem_floats(M, E, a.K, a.n, a.tc_cap, cs, a.wh_rows);
+    f = (f + 3) & ~(size_t)3;
+    f += (size_t)(E + C) * (a.nc1 + 4) + (size_t)C * (a.nc2 + 4) + (size_t)C * (a.nc3 + 4);
+    f = (f + 3) & ~(size_t)3;
+    f += (size_t)3 * DS_ROWS * a.nc2 + 4;
+    if (!a.red_alias) f += red_f;
+    const size_t bytes = f * sizeof(float) + 64;
+    if (bytes <= 227 * 1024) return bytes;
+  }
+  return 0;
 }
 
 int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
@@ -461,7 +470,8 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
   if (a.K < 1 || a.K > 16 || R < 1) return 0;
   int cs = 1;
   while (cs < 8 && R * cs * 2 <= sms && ceil_div(a.Tp, cs * 2) >= 16) cs *= 2;
-  LVSR_CUDA_OK(cudaFuncSetAttribute(dec_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LVSR_CUDA_OK(cudaFuncSetAttribute(dec_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LVSR_CUDA_OK(cudaFuncSetAttribute(dec_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   for (; cs >= 1; cs >>= 1) {
     // prefer islands (grid = one cluster per row); fall back to one global island on all SMs
     bool islands = R >= DS_ROWS;
@@ -491,7 +501,9 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, dec_scan_kernel, &cfg) != cudaSuccess) {
+    const bool compact = a.wh_rows != 16;
+    if ((compact ? cudaOccupancyMaxActiveClusters(&max_clusters, dec_scan_kernel<true>, &cfg)
+                 : cudaOccupancyMaxActiveClusters(&max_clusters, dec_scan_kernel<false>, &cfg)) != cudaSuccess) {
       cudaGetLastError();
       continue;
     }
@@ -512,7 +524,8 @@ int plan_and_launch(DecScanArgs& a, int* supported, cudaStream_t stream) {
       LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_spin_limit, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, stream));
       LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_flow_status, &a.status, sizeof(a.status), 0, cudaMemcpyHostToDevice, stream));
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, dec_scan_kernel, a);
+    cudaError_t e = (a.wh_rows != 16) ? cudaLaunchKernelEx(&cfg, dec_scan_kernel<true>, a)
+                                      : cudaLaunchKernelEx(&cfg, dec_scan_kernel<false>, a);
     if (e != cudaSuccess) {
       cudaGetLastError();
       continue;

@@ -184,6 +184,7 @@ struct DecScanArgs {
   // derived by the planner
   int cs, tc_cap, nrg, nc1, nc2, nc3;
   int nisl, ncg;                       // nisl > 0: islands of <= 16 rows whose CTAs own their dense tiles
+  int wh_rows;                         // handler rows in shared memory: 16 (fast) or K (compact, long utterances)
   int red_alias;                       // dense-tile scratch shares the attention reduction scratch (long utterances)
 };
 int dec_scan_try(DecScanArgs& a, int* supported, cudaStream_t stream);
