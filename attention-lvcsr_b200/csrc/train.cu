@@ -78,13 +78,16 @@ int transpose(const float* src, float* dst, int K, int N, cudaStream_t st) {
 }
 
 int skinny(const float* X0, int K0, int ldx0, const float* W0, const float* X1, int K1, int ldx1, const float* W1,
-           const float* add0, int lda0, const float* add1, int lda1, float* out, int ldo, int R, int N, cudaStream_t st) {
+           const float* add0, int lda0, const float* add1, int lda1, float* out, int ldo, int R, int N, cudaStream_t st,
+           int split = 0, float* out1 = nullptr, int ldo1 = 0) {
   LVSR_CHECK(N % 4 == 0 && K0 % 4 == 0 && (X1 == nullptr || K1 % 4 == 0) && ldx0 % 4 == 0, "skinny: dimensions must be multiples of 4");
   SkinnyArgs a = {};
   a.X[0] = X0; a.K[0] = K0; a.ldx[0] = ldx0; a.W[0] = W0;
   a.X[1] = X1; a.K[1] = K1; a.ldx[1] = ldx1; a.W[1] = W1;
   a.add[0] = add0; a.lda[0] = lda0; a.add[1] = add1; a.lda[1] = lda1;
   a.out = out; a.ldo = ldo; a.R = R; a.N = N;
+  a.split = split; a.out1 = out1; a.ldo1 = ldo1;
+  LVSR_CHECK(split % SK_N == 0, "skinny: the column split must be a multiple of %d", SK_N);
   dim3 grid(ceil_div(N, SK_N), ceil_div(R, SK_R));
   ProfScope prof("skinny", st);
   skinny_kernel<<<grid, SK_WARPS * 32, 0, st>>>(a);
@@ -252,6 +255,12 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
   if (int rc = transpose(m->P(t + "/transition.state_to_state"), WstateT, C, C, st)) return rc;
   if (int rc = transpose(m->P(t + "/transition.state_to_gates"), WgT, C, 2 * C, st)) return rc;
   if (int rc = transpose(m->Wd_cat, WdcatT, E, 3 * C, st)) return rc;
+  // [dG (3C)] . WcombT [3C, C + E] = [ grad of s_{i-1} through the gates | grad of the glimpse ]: one product per step
+  float* WcombT = ws.f32((size_t)3 * C * (C + E));
+  LVSR_CHECK(WcombT, "out of device memory (transposed weights)");
+  LVSR_CUDA_OK(cudaMemsetAsync(WcombT, 0, (size_t)3 * C * (C + E) * sizeof(float), st));
+  if (int rc = copy2d(WcombT, C + E, WgT, C, 2 * C, C, st)) return rc;
+  if (int rc = copy2d(WcombT + C, C + E, WdcatT, E, 3 * C, E, st)) return rc;
   if (int rc = transpose(m->P(at + "/state_trans/transform_states.W"), WsT, C, M, st)) return rc;
   if (int rc = transpose(m->P(at + "/preprocess.W"), WpT, E, M, st)) return rc;
 
@@ -362,9 +371,9 @@ int lvsr_train_cost_and_grads(lvsr_model* m, const float* x, const float* mask, 
       dec_bwd_b_kernel<<<ew, 256, 0, st>>>(dHR, Rg + (size_t)i * B * C, Sp_i, B, C, dG_i, keep);
       LVSR_LAUNCH_CHECK();
       // grad of s_{i-1} through the gates (+ the element-wise paths), grad of the glimpse
-      if (int rc = skinny(dG_i, 2 * C, 3 * C, WgT, nullptr, 0, 0, nullptr, keep, C, nullptr, 0, dspart, C, B, C, st)) return rc;
       float* dctx_i = dCTX + (size_t)i * B * E;
-      if (int rc = skinny(dG_i, 3 * C, 3 * C, WdcatT, nullptr, 0, 0, nullptr, dCtx_ro + (size_t)i * B * E, E, nullptr, 0, dctx_i, E, B, E, st)) return rc;
+      if (int rc = skinny(dG_i, 3 * C, 3 * C, WcombT, nullptr, 0, 0, nullptr, keep, C, dCtx_ro + (size_t)i * B * E, E, dspart, C, B, C + E, st,
+                          C, dctx_i, E)) return rc;
       // attention backward
       const float* w_prev = i == 0 ? w0 : W_all + (size_t)(i - 1) * B * Tp;
       WindowArgs wa = {};

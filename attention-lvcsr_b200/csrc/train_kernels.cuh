@@ -152,6 +152,9 @@ struct SkinnyArgs {
   const float* add[2]; int lda[2];
   float* out; int ldo;
   int R, N;
+  // optional column split: columns >= split go to out1 (ldo1) and take add[1] INSTEAD of add[0] (two products that share
+  // the left-hand side fused into one launch); split = 0: one output, both addends
+  int split; float* out1; int ldo1;
 };
 constexpr int SK_R = 64, SK_N = 8, SK_WARPS = 16;
 
@@ -224,9 +227,19 @@ __global__ void __launch_bounds__(SK_WARPS * 32) skinny_kernel(SkinnyArgs a) {
     float v = 0.f;
 #pragma unroll
     for (int wq = 0; wq < SK_WARPS; ++wq) v += red[wq][o];
-    if (a.add[0]) v += a.add[0][(long long)r * a.lda[0] + c];
-    if (a.add[1]) v += a.add[1][(long long)r * a.lda[1] + c];
-    a.out[(long long)r * a.ldo + c] = v;
+    if (a.split > 0) {
+      if (c < a.split) {
+        if (a.add[0]) v += a.add[0][(long long)r * a.lda[0] + c];
+        a.out[(long long)r * a.ldo + c] = v;
+      } else {
+        if (a.add[1]) v += a.add[1][(long long)r * a.lda[1] + c - a.split];
+        a.out1[(long long)r * a.ldo1 + c - a.split] = v;
+      }
+    } else {
+      if (a.add[0]) v += a.add[0][(long long)r * a.lda[0] + c];
+      if (a.add[1]) v += a.add[1][(long long)r * a.lda[1] + c];
+      a.out[(long long)r * a.ldo + c] = v;
+    }
   }
 }
 
