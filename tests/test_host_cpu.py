@@ -129,3 +129,31 @@ def test_no_gpu_means_loud_failure():
                                post_merge_activation=pkg.Maxout(2))
     with pytest.raises(RuntimeError):
         rec.encode(np.zeros((4, 1, 40), dtype=np.float32))
+
+
+def test_step_rule_chains_map_onto_the_train_config():
+    """algorithms._to_train_config accepts exactly the CompositeRule shapes lvsr/main.py:480-516 can build (in that
+    order) and refuses anything else instead of approximating it."""
+    A = package().algorithms
+    wsj = dict(gradient_threshold=10.0, rules=["momentum", "adadelta"], scale=1.0, momentum=0.0, decay_rate=0.95,
+               epsilon=1e-8, burn_in_steps=3)
+    rule = A.step_rule_from_config(wsj, dict(max_norm=1.0))
+    assert [type(c).__name__ for c in rule.components] == ["StepClipping", "Momentum", "AdaDelta", "Restrict",
+                                                           "RemoveNotFinite", "BurnIn"]
+    tc = A._to_train_config(rule, decay=0.01)
+    assert (tc.gradient_threshold, tc.use_momentum, tc.scale, tc.momentum) == (10.0, 1, 1.0, 0.0)
+    assert tc.use_adadelta == 1 and abs(tc.decay_rate - 0.95) < 1e-7 and abs(tc.epsilon - 1e-8) < 1e-15
+    assert (tc.max_norm, tc.burn_in_steps) == (1.0, 3) and abs(tc.decay - 0.01) < 1e-9
+    proto = A.step_rule_from_config(dict(gradient_threshold=100.0, scale=0.01, momentum=0.0))     # prototype_speech.yaml
+    tc = A._to_train_config(proto)
+    assert (tc.use_momentum, tc.use_adadelta, tc.max_norm, tc.burn_in_steps) == (1, 0, 0.0, 0)
+    with pytest.raises(NotImplementedError):                # AdaDelta before Momentum: not a chain of lvsr/main.py
+        A._to_train_config(A.CompositeRule([A.AdaDelta(), A.Momentum(0.1, 0.0), A.RemoveNotFinite(0.0)]))
+    with pytest.raises(NotImplementedError):                # RemoveNotFinite with another scaler
+        A._to_train_config(A.CompositeRule([A.Momentum(0.1, 0.0), A.RemoveNotFinite(1)]))
+    with pytest.raises(NotImplementedError):                # max-norm over another axis
+        A._to_train_config(A.CompositeRule([A.Restrict(A.VariableClipping(1.0, axis=1), "WEIGHT"), A.RemoveNotFinite(0.0)]))
+    with pytest.raises(ValueError):
+        A.AdaDelta(decay_rate=2.0)                           # B/algorithms/__init__.py:481-482
+    with pytest.raises(ValueError):
+        A.GradientDescent(step_rule=rule)                    # no recognizer: nothing to differentiate
