@@ -25,6 +25,8 @@
 // -> bulk DSMEM copies + mbarrier (3.07 us) -> k over 8 lanes, FFMA2 (2.76 us) -> k over 16 lanes, 4 CTAs x 16 warps,
 // st.async from registers (2.34 us in the loop, 2.67 us/step with launch and staging): the products are bound by the
 // shared-memory return path of the h loads, the rest is lock-step latency (profiles/r1g_summary.md).
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace lvsr {
@@ -35,8 +37,10 @@ constexpr int RB = 4;        // batch rows per cluster
 
 // LVSR_BIGRU_TRACE=1: thread 0 of CTA 0 accumulates the SM clock spent in each section of a step
 // (wait h, gate product, gate epilogue + send, wait h*r, candidate product, epilogue + send).
-__device__ unsigned long long g_bigru_trace[8];
+__device__ unsigned long long g_bigru_trace[12];
 __device__ int g_bigru_trace_on = 0;
+// per CTA: cycles from kernel entry to the first step, cycles inside the time loop (tensor-core kernel, trace runs only)
+__device__ unsigned long long g_bigru_cta_cycles[2][1024];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -419,10 +423,451 @@ int launch_bigru_t(const BiGruArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// =====================================================================================================
+// Tensor-core variant of the same scan (D = 256 at the metric batch): the two recurrent products run on
+// mma.sync m16n8k16 (fp16 operands, fp32 accumulate) with the WEIGHT COLUMNS as the M dimension and the
+// cluster's RB = 4 batch rows in the N = 8 slot (half of it padding): a CTA's 192 columns are 12 M tiles.
+//
+// fp32 accuracy from fp16 operands: every operand is split into an fp16 head and an fp16 tail scaled by
+// 2^11 (x = head + tail / 2048; both exact to ~2^-22 of x), and head*head + (head*tail + tail*head) / 2048
+// is accumulated in fp32 -- three MMAs per 16 k, the same error class as the 3xTF32 GEMMs but at twice the
+// MAC rate of tf32 (measured: 2.0 cycles per m16n8k8 tf32 MMA and SM, tools/micro/mma_rate.cu).
+// Weights are split once (gate slice: 64 registers per lane; state_to_state slice: shared memory, laid out
+// as ready-made A fragments).  h and h*r are split by the SENDER: the all-gather ships, for every pair of
+// units, one word of packed heads and one word of packed tails (same 4 bytes per unit as fp32), so a B
+// fragment of a receiver is one 16-byte shared-memory load per k-step.  The fp32 state itself never leaves
+// the registers of its owner threads: the split only feeds the products.
+//
+// Work split: gate tiles 8 x 2 k-halves, candidate tiles 4 x 4 k-quarters over the 16 warps; partial sums
+// meet in shared memory (one block barrier per phase), then thread (row, 4 units, peer) adds them, applies
+// the non-linearity and ships 16 bytes with one st.async -- the exchange protocol is the FFMA kernel's.
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr float kTailScale = 2048.f, kTailUnscale = 1.f / 2048.f;
+// (x, y) -> packed fp16 heads and packed scaled fp16 tails; the lower half of a word is the lower k index
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& head, uint32_t& tail) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x - hf.x) * kTailScale, (y - hf.y) * kTailScale);
+  head = *reinterpret_cast<const uint32_t*>(&h);
+  tail = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void st_async_v4_b32(uint32_t remote_addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w,
+                                                uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(
+                   remote_addr),
+               "r"(x), "r"(y), "r"(z), "r"(w), "r"(remote_bar)
+               : "memory");
+}
+
+constexpr int MMA_CS = 4, MMA_NWARP = 16;
+template <int D>
+constexpr size_t bigru_mma_dyn_smem() {
+  return (size_t)MMA_NWARP * ((D / 16) / (MMA_NWARP / (D / MMA_CS / 16))) * 2 * 32 * sizeof(uint4);
+}
+
+template <int D, bool TAPE>
+__global__ void __launch_bounds__(MMA_NWARP * 32, 1)
+bigru_mma_kernel(BiGruArgs a) {
+  constexpr int CS = MMA_CS, NWARP = MMA_NWARP;
+  constexpr int UC = D / CS;            // units owned by this CTA
+  constexpr int MT1 = 2 * UC / 16;      // gate tiles: [z units | r units]
+  constexpr int MT2 = UC / 16;          // candidate tiles
+  constexpr int KS1 = NWARP / MT1;      // k splits of a gate tile over warps
+  constexpr int KS2 = NWARP / MT2;
+  constexpr int NK = D / 16;            // k-steps of a full product
+  constexpr int NK1 = NK / KS1, NK2 = NK / KS2;
+  constexpr int UG = UC / 4;            // 4-unit groups of this CTA
+  static_assert(MT1 * KS1 == NWARP && MT2 * KS2 == NWARP && NK1 * KS1 == NK && NK2 * KS2 == NK, "tile split");
+  static_assert(2 * RB * UG <= NWARP * 32, "elementwise roles");
+  // a row of h / h*r: word 2j = packed heads of units (2j, 2j+1), word 2j+1 = their packed tails; +16 words so
+  // that the two rows an 8-lane load phase touches sit in different bank halves
+  constexpr int RS = D + 16;
+  constexpr int RS1 = 2 * UC + 4, RS2 = UC + 4;   // 2 * RS mod 32 = 8: the four row pairs of a C fragment spread over the banks
+  constexpr uint32_t FULL_BYTES = RB * D * sizeof(uint32_t);
+
+  __shared__ __align__(128) uint32_t hbuf[RB][RS];
+  __shared__ __align__(128) uint32_t hrbuf[RB][RS];
+  __shared__ __align__(16) float red1[KS1][RB][RS1];
+  __shared__ __align__(16) float red2[KS2][RB][RS2];
+  __shared__ __align__(16) float zbuf[RB][UC];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  extern __shared__ __align__(16) uint4 w2frag[];   // [warp][NK2][head | tail][lane]
+
+  const long long t_entry = clock64();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int cluster_id = blockIdx.x / CS;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const int dir = cluster_id & 1;
+  const int row0 = (cluster_id >> 1) * RB;
+  const float* Wg = dir ? a.Wg_b : a.Wg_f;
+  const float* Ws = dir ? a.Ws_b : a.Ws_f;
+  const float* h0 = dir ? a.h0_b : a.h0_f;
+
+  // ---- weights -> A fragments (once) ----------------------------------------------------------
+  // MMA k index kk of k-step ks <-> unit 16 ks + 4 (kk/2 % 4) + 2 (kk / 8) + kk % 2: lane tq then needs the
+  // four consecutive units 16 ks + 4 tq .. + 3 of a row, i.e. one 16-byte load of [heads | tails | heads | tails]
+  const int mt1 = warp % MT1, kh = warp / MT1;
+  const int mt2 = warp % MT2, kq = warp / MT2;
+  uint32_t wg_head[NK1][4], wg_tail[NK1][4];
+#pragma unroll
+  for (int j = 0; j < NK1; ++j) {
+    const int k0 = (kh * NK1 + j) * 16 + 4 * tq;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
+      const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
+      split_pair(Wg[(long long)k0 * (2 * D) + col], Wg[(long long)(k0 + 1) * (2 * D) + col], wg_head[j][half],
+                 wg_tail[j][half]);
+      split_pair(Wg[(long long)(k0 + 2) * (2 * D) + col], Wg[(long long)(k0 + 3) * (2 * D) + col], wg_head[j][2 + half],
+                 wg_tail[j][2 + half]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NK2; ++j) {
+    const int k0 = (kq * NK2 + j) * 16 + 4 * tq;
+    uint32_t hd[4], tl[4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const long long col = rank * UC + 16 * mt2 + g + 8 * half;
+      split_pair(Ws[(long long)k0 * D + col], Ws[(long long)(k0 + 1) * D + col], hd[half], tl[half]);
+      split_pair(Ws[(long long)(k0 + 2) * D + col], Ws[(long long)(k0 + 3) * D + col], hd[2 + half], tl[2 + half]);
+    }
+    w2frag[((warp * NK2 + j) * 2 + 0) * 32 + lane] = make_uint4(hd[0], hd[1], hd[2], hd[3]);
+    w2frag[((warp * NK2 + j) * 2 + 1) * 32 + lane] = make_uint4(tl[0], tl[1], tl[2], tl[3]);
+  }
+  for (int i = tid; i < RB * D / 2; i += NWARP * 32) {
+    const int r = i / (D / 2), j = i % (D / 2);
+    split_pair(h0[2 * j], h0[2 * j + 1], hbuf[r][2 * j], hbuf[r][2 * j + 1]);
+  }
+
+  // ---- elementwise roles: thread (gate kind, row, 4 units) ------------------------------------------
+  // threads [0, RB * UG) own (row, 4 units): reset gate -> h * r -> send, later candidate -> h' -> send (one st.async per
+  // peer); threads [RB * UG, 2 RB UG) compute the update gate of the same (row, 4 units) meanwhile and park it in zbuf.
+  // Every value is computed ONCE per CTA: the MUFU pipe (16 lanes per clock and SM) is what an epilogue waits for.
+  const bool gate_role = tid < 2 * RB * UG;
+  const bool epi = tid < RB * UG;            // reset gate + candidate + sends
+  const bool zrole = gate_role && !epi;      // update gate
+  const int rid = tid % (RB * UG);
+  const int ug = rid % UG, erow = gate_role ? rid / UG : 0;
+  const int u_loc = 4 * ug, u_glob = rank * UC + u_loc;
+  const bool row_ok = gate_role && row0 + erow < a.B;
+  const bool writer = row_ok;
+  const int goff = epi ? UC : 0;             // column of this thread's gate in red1: [z units | r units]
+  const uint32_t bar_h = smem_u32(&mbar[0]), bar_hr = smem_u32(&mbar[1]);
+  const uint32_t loc_h = smem_u32(&hbuf[erow][u_glob]), loc_hr = smem_u32(&hrbuf[erow][u_glob]);
+  if (tid == 0) {
+    mbar_init(bar_h, 1);
+    mbar_init(bar_hr, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  float h_own[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h_own[i] = h0[u_glob + i];
+  if constexpr (TAPE) {
+    if (writer && epi)
+      *reinterpret_cast<float4*>(a.hext + ((long long)(dir ? a.T + 1 : 0) * a.B + row0 + erow) * (2 * D) + dir * D + u_glob) =
+          make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
+  }
+
+  const int T = a.T, B = a.B;
+  const long long pre_ld = 6LL * D;
+  const int dt = dir ? -1 : 1;
+  int t = dir ? (T - 1) : 0;
+  // fork pre-activations of this thread's 4 units: [inputs | update | reset]; every slot is re-loaded for the next
+  // step right after its consumer, so a load has most of a step to land and nothing is double-buffered
+  const long long pre_off = ((long long)t * B + row0 + erow) * pre_ld + (long long)dir * 3 * D + u_glob;
+  const float* pre_ptr = a.pre + pre_off;
+  float* tape_ptr = TAPE ? a.tape + pre_off : nullptr;
+  const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + erow : nullptr;
+  const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int gslot = epi ? 2 * D : D;       // this thread's gate slot of the pre-activations / tape
+  float4 pa = zero4, pg = zero4;
+  float pm = 1.f;
+  if (row_ok) {
+    pg = __ldg(reinterpret_cast<const float4*>(pre_ptr + gslot));
+    if (epi) {
+      pa = __ldg(reinterpret_cast<const float4*>(pre_ptr));
+      if (pm_ptr) pm = __ldg(pm_ptr);
+    }
+  }
+
+  __syncthreads();
+  cluster_sync_all();
+
+  int sub_phase = dir ? ((T - 1) % a.subsample) : 0;
+  int t_out = t / a.subsample;
+  const bool tracer = g_bigru_trace_on && blockIdx.x == 0 && tid == 0;
+  const long long t_loop = clock64();
+  // section clocks live in shared memory: only one thread ever touches them and registers are the scarce resource here
+  __shared__ unsigned long long tr[11];   // [6]: last clock, [7] / [8]: block-barrier waits of the two phases
+  if (tracer)
+    for (int j = 0; j < 11; ++j) tr[j] = 0;
+#define BG_STAMP(j)                                  \
+  do {                                               \
+    if (tracer) {                                    \
+      const unsigned long long now = clock64();      \
+      tr[j] += now - tr[6];                          \
+      tr[6] = now;                                   \
+    }                                                \
+  } while (0)
+  // B fragments: N column g of the MMA is batch row g; the columns 4..7 are padding -- their lanes simply re-read
+  // rows 0..3 (same addresses: a broadcast, no extra shared-memory traffic) and their results are never stored
+  const uint4* hb4 = reinterpret_cast<const uint4*>(&hbuf[g % RB][kh * NK1 * 16 + 4 * tq]);
+  const uint4* hrb4 = reinterpret_cast<const uint4*>(&hrbuf[g % RB][kq * NK2 * 16 + 4 * tq]);
+  const uint4* w2f = &w2frag[warp * NK2 * 2 * 32 + lane];
+  for (int s = 0; s < T; ++s, t += dt) {
+    const bool more = s + 1 < T;
+    if (tracer) tr[6] = clock64();
+    if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
+    if (tid == 0) {
+      mbar_arm(bar_h, FULL_BYTES);
+      mbar_arm(bar_hr, FULL_BYTES);
+    }
+    BG_STAMP(0);
+
+    // ---- phase 1: gate tile mt1, k-steps [kh * NK1, +NK1) ---------------------------------------
+    {
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NK1; ++j) {
+        const uint4 v = hb4[j * 4];
+        mma_f16(c0, wg_head[j], v.x, v.z);
+        mma_f16(c1, wg_head[j], v.y, v.w);
+        mma_f16(c2, wg_tail[j], v.x, v.z);
+      }
+      if (tq < RB / 2) {
+        float* o = &red1[kh][2 * tq][mt1 * 16 + g];
+        o[0] = c0[0] + (c1[0] + c2[0]) * kTailUnscale;
+        o[RS1] = c0[1] + (c1[1] + c2[1]) * kTailUnscale;
+        o[8] = c0[2] + (c1[2] + c2[2]) * kTailUnscale;
+        o[RS1 + 8] = c0[3] + (c1[3] + c2[3]) * kTailUnscale;
+      }
+    }
+    BG_STAMP(1);
+    __syncthreads();
+    BG_STAMP(7);
+    if (gate_role) {
+      float sg[4] = {pg.x, pg.y, pg.z, pg.w};
+#pragma unroll
+      for (int k = 0; k < KS1; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(&red1[k][erow][goff + u_loc]);
+        sg[0] += x.x; sg[1] += x.y; sg[2] += x.z; sg[3] += x.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sg[i] = fast_sigmoid(sg[i]);
+      if (epi) {
+        uint32_t w0, w1, w2, w3;
+        split_pair(h_own[0] * sg[0], h_own[1] * sg[1], w0, w1);
+        split_pair(h_own[2] * sg[2], h_own[3] * sg[3], w2, w3);
+#pragma unroll
+        for (int p = 0; p < CS; ++p) st_async_v4_b32(map_to_rank(loc_hr, p), w0, w1, w2, w3, map_to_rank(bar_hr, p));
+      } else {
+        *reinterpret_cast<float4*>(&zbuf[erow][u_loc]) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      }
+      if constexpr (TAPE) {
+        if (writer) *reinterpret_cast<float4*>(tape_ptr + gslot) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      }
+      if (more && row_ok) pg = __ldg(reinterpret_cast<const float4*>(pre_ptr + pre_step + gslot));
+    }
+    BG_STAMP(2);
+
+    // ---- phase 2: candidate tile mt2, k-steps [kq * NK2, +NK2) ----------------------------------
+    mbar_wait(bar_hr, (uint32_t)(s & 1));
+    BG_STAMP(3);
+    {
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NK2; ++j) {
+        const uint4 ah = w2f[(j * 2 + 0) * 32];
+        const uint4 at = w2f[(j * 2 + 1) * 32];
+        const uint32_t fh[4] = {ah.x, ah.y, ah.z, ah.w}, ft[4] = {at.x, at.y, at.z, at.w};
+        const uint4 v = hrb4[j * 4];
+        mma_f16(c0, fh, v.x, v.z);
+        mma_f16(c1, fh, v.y, v.w);
+        mma_f16(c2, ft, v.x, v.z);
+      }
+      if (tq < RB / 2) {
+        float* o = &red2[kq][2 * tq][mt2 * 16 + g];
+        o[0] = c0[0] + (c1[0] + c2[0]) * kTailUnscale;
+        o[RS2] = c0[1] + (c1[1] + c2[1]) * kTailUnscale;
+        o[8] = c0[2] + (c1[2] + c2[2]) * kTailUnscale;
+        o[RS2 + 8] = c0[3] + (c1[3] + c2[3]) * kTailUnscale;
+      }
+    }
+    BG_STAMP(4);
+    __syncthreads();
+    BG_STAMP(8);
+    if (epi) {
+      float sc[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+      for (int k = 0; k < KS2; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(&red2[k][erow][u_loc]);
+        sc[0] += x.x; sc[1] += x.y; sc[2] += x.z; sc[3] += x.w;
+      }
+      const float4 z4 = *reinterpret_cast<const float4*>(&zbuf[erow][u_loc]);
+      const float zg[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sc[i] = fast_tanh(sc[i]);
+        float hn = sc[i] * zg[i] + h_own[i] * (1.f - zg[i]);
+        hn = pm * hn + (1.f - pm) * h_own[i];
+        h_own[i] = hn;
+      }
+      uint32_t w0, w1, w2, w3;
+      split_pair(h_own[0], h_own[1], w0, w1);
+      split_pair(h_own[2], h_own[3], w2, w3);
+      BG_STAMP(9);
+#pragma unroll
+      for (int p = 0; p < CS; ++p) st_async_v4_b32(map_to_rank(loc_h, p), w0, w1, w2, w3, map_to_rank(bar_h, p));
+      BG_STAMP(10);
+      if (writer) {
+        const float4 hv = make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
+        if (sub_phase == 0)
+          *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
+        if constexpr (TAPE) {
+          *reinterpret_cast<float4*>(tape_ptr) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+          *reinterpret_cast<float4*>(a.hext + ((long long)(t + 1) * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
+        }
+      }
+    }
+    if (gate_role) {
+      pre_ptr += pre_step;
+      if constexpr (TAPE) tape_ptr += pre_step;
+      if (epi) {
+        if (pm_ptr) pm_ptr += mask_step;
+        if (more && row_ok) {
+          pa = __ldg(reinterpret_cast<const float4*>(pre_ptr));
+          if (pm_ptr) pm = __ldg(pm_ptr);
+        }
+      }
+    }
+    BG_STAMP(5);
+    if (dir == 0) {
+      if (++sub_phase == a.subsample) { sub_phase = 0; ++t_out; }
+    } else {
+      if (sub_phase == 0) { sub_phase = a.subsample - 1; --t_out; } else { --sub_phase; }
+    }
+  }
+#undef BG_STAMP
+  if (g_bigru_trace_on && tid == 32 && blockIdx.x < 1024) {   // a thread without an elementwise role
+    g_bigru_cta_cycles[0][blockIdx.x] = (unsigned long long)(t_loop - t_entry);
+    g_bigru_cta_cycles[1][blockIdx.x] = (unsigned long long)(clock64() - t_loop);
+  }
+  if (tracer) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) g_bigru_trace[j] = tr[j];
+    g_bigru_trace[6] = (unsigned long long)T;
+    g_bigru_trace[7] = tr[7];
+    g_bigru_trace[8] = tr[8];
+    g_bigru_trace[9] = tr[9];
+    g_bigru_trace[10] = tr[10];
+  }
+  mbar_wait(bar_h, (uint32_t)((T - 1) & 1));
+  cluster_sync_all();
+}
+
 template <int D, int CS, int NWARP>
 int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
   LVSR_CHECK((a.tape == nullptr) == (a.hext == nullptr), "bigru: tape and hext go together");
   return a.tape ? launch_bigru_t<D, CS, NWARP, true>(a, stream) : launch_bigru_t<D, CS, NWARP, false>(a, stream);
+}
+
+template <int D, bool TAPE>
+int mma_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int clusters, cudaStream_t stream) {
+  static bool configured[LVSR_MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_mma_kernel<D, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)bigru_mma_dyn_smem<D>()));
+    configured[dev] = true;
+  }
+  cfg = {};
+  cfg.gridDim = dim3(MMA_CS * clusters);
+  cfg.blockDim = dim3(MMA_NWARP * 32);
+  cfg.dynamicSmemBytes = bigru_mma_dyn_smem<D>();
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MMA_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return 0;
+}
+
+template <int D, bool TAPE>
+int launch_bigru_mma_t(const BiGruArgs& a, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  if (int rc = mma_launch_config<D, TAPE>(cfg, attr, ceil_div(a.B, RB) * 2, stream)) return rc;
+  static const bool trace = getenv("LVSR_BIGRU_TRACE") != nullptr;
+  if (trace) {
+    const int on = 1;
+    LVSR_CUDA_OK(cudaMemcpyToSymbolAsync(g_bigru_trace_on, &on, sizeof(on), 0, cudaMemcpyHostToDevice, stream));
+  }
+  LVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, bigru_mma_kernel<D, TAPE>, a));
+  g_launch_count++;
+  if (trace) {
+    unsigned long long h[12] = {0};
+    LVSR_CUDA_OK(cudaMemcpyFromSymbolAsync(h, g_bigru_trace, sizeof(h), 0, cudaMemcpyDeviceToHost, stream));
+    LVSR_CUDA_OK(cudaStreamSynchronize(stream));
+    const double n = h[6] ? (double)h[6] : 1.0;
+    fprintf(stderr,
+            "[bigru trace] mma<%d> T=%llu cycles/step: wait_h=%.0f gates=%.0f barrier=%.0f gate_epi+send=%.0f wait_hr=%.0f "
+            "cand=%.0f barrier=%.0f cand_math=%.0f sends=%.0f stores+prefetch=%.0f\n",
+            D, h[6], h[0] / n, h[1] / n, h[7] / n, h[2] / n, h[3] / n, h[4] / n, h[8] / n, h[9] / n, h[10] / n, h[5] / n);
+    static unsigned long long cc[2][1024];
+    LVSR_CUDA_OK(cudaMemcpyFromSymbol(cc, g_bigru_cta_cycles, sizeof(cc)));
+    const int nc = (int)cfg.gridDim.x < 1024 ? (int)cfg.gridDim.x : 1024;
+    for (int w = 0; w < 2; ++w) {
+      unsigned long long lo = ~0ull, hi = 0;
+      double sum = 0;
+      for (int c = 0; c < nc; ++c) {
+        lo = cc[w][c] < lo ? cc[w][c] : lo;
+        hi = cc[w][c] > hi ? cc[w][c] : hi;
+        sum += (double)cc[w][c];
+      }
+      fprintf(stderr, "[bigru trace]   %s cycles per CTA: min %llu avg %.0f max %llu%s\n", w ? "loop" : "entry->loop", lo, sum / nc, hi,
+              w ? "" : "");
+    }
+    fprintf(stderr, "[bigru trace]   loop cycles per step, slowest CTA: %.0f\n", 0.0 + (double)[&] { unsigned long long m = 0; for (int c = 0; c < nc; ++c) m = cc[1][c] > m ? cc[1][c] : m; return m; }() / n);
+  }
+  return 0;
+}
+
+template <int D>
+int launch_bigru_mma(const BiGruArgs& a, cudaStream_t stream) {
+  LVSR_CHECK((a.tape == nullptr) == (a.hext == nullptr), "bigru: tape and hext go together");
+  return a.tape ? launch_bigru_mma_t<D, true>(a, stream) : launch_bigru_mma_t<D, false>(a, stream);
+}
+
+// how many clusters of the tensor-core kernel the device holds at once (one CTA per SM, 4 SMs of one GPC per cluster)
+template <int D>
+int mma_clusters_resident() {
+  static int per_dev[LVSR_MAX_DEVICES];
+  static bool known[LVSR_MAX_DEVICES] = {false};
+  const int dev = current_device();
+  if (!known[dev]) {
+    known[dev] = true;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int k = 0;
+    if (mma_launch_config<D, false>(cfg, attr, 64, nullptr) != 0 ||
+        cudaOccupancyMaxActiveClusters(&k, bigru_mma_kernel<D, false>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      k = 0;
+    }
+    per_dev[dev] = k;
+  }
+  return per_dev[dev];
 }
 
 int bigru_sm_count() { return device_sm_count(); }
@@ -473,6 +918,10 @@ int bigru_layer(const BiGruArgs& a, cudaStream_t stream) {
   const int groups = ceil_div(a.B, RB);
   bool wide = a.D == 256 && 8 * groups * 2 > bigru_sm_count() && groups * 2 <= wide_clusters_resident();
   if (const char* e = getenv("LVSR_BIGRU_WIDE")) wide = a.D == 256 && atoi(e) != 0;
+  // tensor-core products whenever every cluster gets four SMs of its own (otherwise the launch runs in waves)
+  bool mma = a.D == 256 && groups * 2 <= mma_clusters_resident<256>();
+  if (const char* e = getenv("LVSR_BIGRU_MMA")) mma = a.D == 256 && atoi(e) != 0;
+  if (mma) return launch_bigru_mma<256>(a, stream);
   switch (a.D) {
     case 128: return launch_bigru<128, 4, 8>(a, stream);
     case 256: return wide ? launch_bigru<256, 4, 16>(a, stream) : launch_bigru<256, 8, 8>(a, stream);
