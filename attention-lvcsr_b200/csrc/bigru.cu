@@ -426,21 +426,30 @@ int launch_bigru_t(const BiGruArgs& a, cudaStream_t stream) {
 // =====================================================================================================
 // Tensor-core variant of the same scan (D = 256 at the metric batch): the two recurrent products run on
 // mma.sync m16n8k16 (fp16 operands, fp32 accumulate) with the WEIGHT COLUMNS as the M dimension and the
-// cluster's RB = 4 batch rows in the N = 8 slot (half of it padding): a CTA's 192 columns are 12 M tiles.
+// cluster's RB = 4 batch rows in the N = 8 slot: a CTA's 192 columns are 12 M tiles.
 //
 // fp32 accuracy from fp16 operands: every operand is split into an fp16 head and an fp16 tail scaled by
-// 2^11 (x = head + tail / 2048; both exact to ~2^-22 of x), and head*head + (head*tail + tail*head) / 2048
-// is accumulated in fp32 -- three MMAs per 16 k, the same error class as the 3xTF32 GEMMs but at twice the
-// MAC rate of tf32 (measured: 2.0 cycles per m16n8k8 tf32 MMA and SM, tools/micro/mma_rate.cu).
-// Weights are split once (gate slice: 64 registers per lane; state_to_state slice: shared memory, laid out
-// as ready-made A fragments).  h and h*r are split by the SENDER: the all-gather ships, for every pair of
-// units, one word of packed heads and one word of packed tails (same 4 bytes per unit as fp32), so a B
-// fragment of a receiver is one 16-byte shared-memory load per k-step.  The fp32 state itself never leaves
-// the registers of its owner threads: the split only feeds the products.
+// 2^11 (x = head + tail / 2048; both exact to ~2^-22 of x) and
+//     head_w * head_h + (head_w * tail_h + tail_w * head_h) / 2048
+// is accumulated in fp32 -- the error class of the 3xTF32 GEMMs at twice the MAC rate of tf32 (measured: 2.0 cycles
+// per m16n8k8-tf32 or m16n8k16-f16 MMA and SM, tools/micro/mma_rate.cu).  It takes TWO MMAs per 16 k, not three: the
+// N columns 0..3 of the B operand carry the heads of the four rows and the columns 4..7 their tails, so
+// A = head_w yields head*head and head*tail in one instruction; the second one has A = tail_w.
+// Weights are split once and stay in registers as ready-made A fragments (192 per lane).  h and h*r are split by the
+// SENDER: the all-gather ships packed heads into one plane of the receiver's buffer and packed tails into another
+// (4 bytes per unit in total, as fp32 would), so a B fragment is one 8-byte shared-memory load per k-step.  The
+// fp32 state itself never leaves the registers of its owner threads: the split only feeds the products.
 //
-// Work split: gate tiles 8 x 2 k-halves, candidate tiles 4 x 4 k-quarters over the 16 warps; partial sums
-// meet in shared memory (one block barrier per phase), then thread (row, 4 units, peer) adds them, applies
-// the non-linearity and ships 16 bytes with one st.async -- the exchange protocol is the FFMA kernel's.
+// Warp specialisation (12 warps, one CTA per SM; `setmaxnreg` moves registers from the elementwise warps to the MMA warps):
+//   warps 4..11  MMA: one gate tile each over the full k, candidate tiles 4 x 2 k-halves; partial sums go to shared memory and
+//                the warp ARRIVES on a named barrier -- it never waits for the elementwise work, only for operands
+//                (mbarrier: all bytes of h / h*r have landed).
+//   warps 0..3   elementwise: wait on the named barrier, add the partial sums + fork pre-activations, non-linearity,
+//                split, one st.async per peer; every value is computed once or twice per CTA (the MUFU pipe is narrow).
+//                Threads [0, 64) own (row, 4 units) and ship the heads, threads [64, 128) recompute the same values,
+//                ship the tails and compute the update gate off the critical path.
+// The exchange protocol is the FFMA kernel's (st.async + complete_tx on the receiver's mbarrier, no cluster barrier
+// in the loop).
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -456,321 +465,338 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& head, uin
   head = *reinterpret_cast<const uint32_t*>(&h);
   tail = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void st_async_v4_b32(uint32_t remote_addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w,
-                                                uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(
-                   remote_addr),
-               "r"(x), "r"(y), "r"(z), "r"(w), "r"(remote_bar)
+__device__ __forceinline__ void st_async_v2_b32(uint32_t remote_addr, uint32_t x, uint32_t y, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n" ::"r"(remote_addr),
+               "r"(x), "r"(y), "r"(remote_bar)
                : "memory");
 }
-
-constexpr int MMA_CS = 4, MMA_NWARP = 16;
-template <int D>
-constexpr size_t bigru_mma_dyn_smem() {
-  return (size_t)MMA_NWARP * ((D / 16) / (MMA_NWARP / (D / MMA_CS / 16))) * 2 * 32 * sizeof(uint4);
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
 
+constexpr int MMA_CS = 4, MMA_WARPS = 8, EW_WARPS = 4, MMA_THREADS = (MMA_WARPS + EW_WARPS) * 32;
+// setmaxnreg redistributes the registers the CTA was LAUNCHED with (384 threads x 168), not the SM's whole file:
+// 256 * 224 + 128 * 56 = 64512 = 384 * 168
+constexpr int MMA_REGS = 224, EW_REGS = 56;
+
 template <int D, bool TAPE>
-__global__ void __launch_bounds__(MMA_NWARP * 32, 1)
+__global__ void __launch_bounds__(MMA_THREADS, 1)
 bigru_mma_kernel(BiGruArgs a) {
-  constexpr int CS = MMA_CS, NWARP = MMA_NWARP;
+  constexpr int CS = MMA_CS;
   constexpr int UC = D / CS;            // units owned by this CTA
   constexpr int MT1 = 2 * UC / 16;      // gate tiles: [z units | r units]
   constexpr int MT2 = UC / 16;          // candidate tiles
-  constexpr int KS1 = NWARP / MT1;      // k splits of a gate tile over warps
-  constexpr int KS2 = NWARP / MT2;
+  constexpr int KS1 = MMA_WARPS / MT1;  // k splits of a gate tile over warps
+  constexpr int KS2 = MMA_WARPS / MT2;
   constexpr int NK = D / 16;            // k-steps of a full product
   constexpr int NK1 = NK / KS1, NK2 = NK / KS2;
   constexpr int UG = UC / 4;            // 4-unit groups of this CTA
-  static_assert(MT1 * KS1 == NWARP && MT2 * KS2 == NWARP && NK1 * KS1 == NK && NK2 * KS2 == NK, "tile split");
-  static_assert(2 * RB * UG <= NWARP * 32, "elementwise roles");
-  // a row of h / h*r: word 2j = packed heads of units (2j, 2j+1), word 2j+1 = their packed tails; +16 words so
-  // that the two rows an 8-lane load phase touches sit in different bank halves
-  constexpr int RS = D + 16;
-  constexpr int RS1 = 2 * UC + 4, RS2 = UC + 4;   // 2 * RS mod 32 = 8: the four row pairs of a C fragment spread over the banks
+  constexpr int NROLE = RB * UG;        // (row, unit group) roles
+  static_assert(MT1 * KS1 == MMA_WARPS && MT2 * KS2 == MMA_WARPS && NK1 * KS1 == NK && NK2 * KS2 == NK, "tile split");
+  static_assert(2 * NROLE <= EW_WARPS * 32, "elementwise roles");
+  static_assert(RB == 4, "N columns: 4 rows of heads + 4 rows of tails");
+  // a plane row: 2 words per 4-unit group = packed (u, u+1), (u+2, u+3); + 8 words: the 16 lanes of a load phase
+  // (4 rows x 4 groups) then cover all 32 banks once
+  constexpr int RSH = D / 2 + 8;
+  constexpr int RS1 = 2 * UC + 4, RS2 = UC + 4;   // 2 * RS mod 32 = 8: the row pairs of a C fragment spread over the banks
   constexpr uint32_t FULL_BYTES = RB * D * sizeof(uint32_t);
 
-  __shared__ __align__(128) uint32_t hbuf[RB][RS];
-  __shared__ __align__(128) uint32_t hrbuf[RB][RS];
+  __shared__ __align__(128) uint32_t hbuf[2][RB][RSH];    // [heads | tails] of h
+  __shared__ __align__(128) uint32_t hrbuf[2][RB][RSH];   // ... of h * r
   __shared__ __align__(16) float red1[KS1][RB][RS1];
   __shared__ __align__(16) float red2[KS2][RB][RS2];
   __shared__ __align__(16) float zbuf[RB][UC];
   __shared__ __align__(8) unsigned long long mbar[2];
-  extern __shared__ __align__(16) uint4 w2frag[];   // [warp][NK2][head | tail][lane]
+  __shared__ unsigned long long tr[12];   // section clocks of the two traced threads (only they touch them)
 
   const long long t_entry = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, tq = lane & 3;
   const int cluster_id = blockIdx.x / CS;
   unsigned rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
   const int dir = cluster_id & 1;
   const int row0 = (cluster_id >> 1) * RB;
-  const float* Wg = dir ? a.Wg_b : a.Wg_f;
-  const float* Ws = dir ? a.Ws_b : a.Ws_f;
   const float* h0 = dir ? a.h0_b : a.h0_f;
-
-  // ---- weights -> A fragments (once) ----------------------------------------------------------
-  // MMA k index kk of k-step ks <-> unit 16 ks + 4 (kk/2 % 4) + 2 (kk / 8) + kk % 2: lane tq then needs the
-  // four consecutive units 16 ks + 4 tq .. + 3 of a row, i.e. one 16-byte load of [heads | tails | heads | tails]
-  const int mt1 = warp % MT1, kh = warp / MT1;
-  const int mt2 = warp % MT2, kq = warp / MT2;
-  uint32_t wg_head[NK1][4], wg_tail[NK1][4];
-#pragma unroll
-  for (int j = 0; j < NK1; ++j) {
-    const int k0 = (kh * NK1 + j) * 16 + 4 * tq;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
-      const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
-      split_pair(Wg[(long long)k0 * (2 * D) + col], Wg[(long long)(k0 + 1) * (2 * D) + col], wg_head[j][half],
-                 wg_tail[j][half]);
-      split_pair(Wg[(long long)(k0 + 2) * (2 * D) + col], Wg[(long long)(k0 + 3) * (2 * D) + col], wg_head[j][2 + half],
-                 wg_tail[j][2 + half]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NK2; ++j) {
-    const int k0 = (kq * NK2 + j) * 16 + 4 * tq;
-    uint32_t hd[4], tl[4];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const long long col = rank * UC + 16 * mt2 + g + 8 * half;
-      split_pair(Ws[(long long)k0 * D + col], Ws[(long long)(k0 + 1) * D + col], hd[half], tl[half]);
-      split_pair(Ws[(long long)(k0 + 2) * D + col], Ws[(long long)(k0 + 3) * D + col], hd[2 + half], tl[2 + half]);
-    }
-    w2frag[((warp * NK2 + j) * 2 + 0) * 32 + lane] = make_uint4(hd[0], hd[1], hd[2], hd[3]);
-    w2frag[((warp * NK2 + j) * 2 + 1) * 32 + lane] = make_uint4(tl[0], tl[1], tl[2], tl[3]);
-  }
-  for (int i = tid; i < RB * D / 2; i += NWARP * 32) {
-    const int r = i / (D / 2), j = i % (D / 2);
-    split_pair(h0[2 * j], h0[2 * j + 1], hbuf[r][2 * j], hbuf[r][2 * j + 1]);
-  }
-
-  // ---- elementwise roles: thread (gate kind, row, 4 units) ------------------------------------------
-  // threads [0, RB * UG) own (row, 4 units): reset gate -> h * r -> send, later candidate -> h' -> send (one st.async per
-  // peer); threads [RB * UG, 2 RB UG) compute the update gate of the same (row, 4 units) meanwhile and park it in zbuf.
-  // Every value is computed ONCE per CTA: the MUFU pipe (16 lanes per clock and SM) is what an epilogue waits for.
-  const bool gate_role = tid < 2 * RB * UG;
-  const bool epi = tid < RB * UG;            // reset gate + candidate + sends
-  const bool zrole = gate_role && !epi;      // update gate
-  const int rid = tid % (RB * UG);
-  const int ug = rid % UG, erow = gate_role ? rid / UG : 0;
-  const int u_loc = 4 * ug, u_glob = rank * UC + u_loc;
-  const bool row_ok = gate_role && row0 + erow < a.B;
-  const bool writer = row_ok;
-  const int goff = epi ? UC : 0;             // column of this thread's gate in red1: [z units | r units]
   const uint32_t bar_h = smem_u32(&mbar[0]), bar_hr = smem_u32(&mbar[1]);
-  const uint32_t loc_h = smem_u32(&hbuf[erow][u_glob]), loc_hr = smem_u32(&hrbuf[erow][u_glob]);
+  const int T = a.T, B = a.B;
+
+  for (int i = tid; i < RB * D / 2; i += MMA_THREADS) {
+    const int r = i / (D / 2), j = i % (D / 2);
+    split_pair(h0[2 * j], h0[2 * j + 1], hbuf[0][r][j], hbuf[1][r][j]);
+  }
   if (tid == 0) {
     mbar_init(bar_h, 1);
     mbar_init(bar_hr, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    for (int j = 0; j < 12; ++j) tr[j] = 0;
   }
-  float h_own[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h_own[i] = h0[u_glob + i];
-  if constexpr (TAPE) {
-    if (writer && epi)
-      *reinterpret_cast<float4*>(a.hext + ((long long)(dir ? a.T + 1 : 0) * a.B + row0 + erow) * (2 * D) + dir * D + u_glob) =
-          make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
-  }
-
-  const int T = a.T, B = a.B;
-  const long long pre_ld = 6LL * D;
-  const int dt = dir ? -1 : 1;
-  int t = dir ? (T - 1) : 0;
-  // fork pre-activations of this thread's 4 units: [inputs | update | reset]; every slot is re-loaded for the next
-  // step right after its consumer, so a load has most of a step to land and nothing is double-buffered
-  const long long pre_off = ((long long)t * B + row0 + erow) * pre_ld + (long long)dir * 3 * D + u_glob;
-  const float* pre_ptr = a.pre + pre_off;
-  float* tape_ptr = TAPE ? a.tape + pre_off : nullptr;
-  const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + erow : nullptr;
-  const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int gslot = epi ? 2 * D : D;       // this thread's gate slot of the pre-activations / tape
-  float4 pa = zero4, pg = zero4;
-  float pm = 1.f;
-  if (row_ok) {
-    pg = __ldg(reinterpret_cast<const float4*>(pre_ptr + gslot));
-    if (epi) {
-      pa = __ldg(reinterpret_cast<const float4*>(pre_ptr));
-      if (pm_ptr) pm = __ldg(pm_ptr);
-    }
-  }
-
+  // every CTA of the cluster must be resident (and its mbarriers initialised) before any remote copy is issued
   __syncthreads();
   cluster_sync_all();
-
-  int sub_phase = dir ? ((T - 1) % a.subsample) : 0;
-  int t_out = t / a.subsample;
-  const bool tracer = g_bigru_trace_on && blockIdx.x == 0 && tid == 0;
+  const bool tracing = g_bigru_trace_on && blockIdx.x == 0;
   const long long t_loop = clock64();
-  // section clocks live in shared memory: only one thread ever touches them and registers are the scarce resource here
-  __shared__ unsigned long long tr[11];   // [6]: last clock, [7] / [8]: block-barrier waits of the two phases
-  if (tracer)
-    for (int j = 0; j < 11; ++j) tr[j] = 0;
-#define BG_STAMP(j)                                  \
-  do {                                               \
-    if (tracer) {                                    \
-      const unsigned long long now = clock64();      \
-      tr[j] += now - tr[6];                          \
-      tr[6] = now;                                   \
-    }                                                \
+
+  if (warp >= EW_WARPS) {
+    // =================================== MMA warps ===================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(MMA_REGS));
+    const int g = lane >> 2, tq = lane & 3;
+    const int m = warp - EW_WARPS;
+    const int mt1 = m % MT1, kh = m / MT1;
+    const int mt2 = m % MT2, kq = m / MT2;
+    const float* Wg = dir ? a.Wg_b : a.Wg_f;
+    const float* Ws = dir ? a.Ws_b : a.Ws_f;
+    // ---- weights -> A fragments (once).  MMA k index kk of k-step ks <-> unit 16 ks + 4 (kk/2 % 4) + 2 (kk / 8) + kk % 2:
+    // lane tq then needs the packed pairs of the four consecutive units 16 ks + 4 tq .. + 3 of a row = 8 bytes of a plane
+    uint32_t wg_head[NK1][4], wg_tail[NK1][4], ws_head[NK2][4], ws_tail[NK2][4];
+#pragma unroll
+    for (int j = 0; j < NK1; ++j) {
+      const int k0 = (kh * NK1 + j) * 16 + 4 * tq;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
+        const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
+        split_pair(Wg[(long long)k0 * (2 * D) + col], Wg[(long long)(k0 + 1) * (2 * D) + col], wg_head[j][half],
+                   wg_tail[j][half]);
+        split_pair(Wg[(long long)(k0 + 2) * (2 * D) + col], Wg[(long long)(k0 + 3) * (2 * D) + col], wg_head[j][2 + half],
+                   wg_tail[j][2 + half]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NK2; ++j) {
+      const int k0 = (kq * NK2 + j) * 16 + 4 * tq;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const long long col = rank * UC + 16 * mt2 + g + 8 * half;
+        split_pair(Ws[(long long)k0 * D + col], Ws[(long long)(k0 + 1) * D + col], ws_head[j][half], ws_tail[j][half]);
+        split_pair(Ws[(long long)(k0 + 2) * D + col], Ws[(long long)(k0 + 3) * D + col], ws_head[j][2 + half],
+                   ws_tail[j][2 + half]);
+      }
+    }
+    // B fragments: N column g < 4 = heads of batch row g, N column g >= 4 = tails of batch row g - 4
+    const uint2* hb2 = reinterpret_cast<const uint2*>(&hbuf[g / RB][g % RB][kh * NK1 * 8 + 2 * tq]);
+    const uint2* hrb2 = reinterpret_cast<const uint2*>(&hrbuf[g / RB][g % RB][kq * NK2 * 8 + 2 * tq]);
+    float* const out1 = &red1[kh][2 * (tq & 1)][mt1 * 16 + g];
+    float* const out2 = &red2[kq][2 * (tq & 1)][mt2 * 16 + g];
+    const bool tracer = tracing && tid == EW_WARPS * 32;
+#define BG_STAMP(j)                              \
+  do {                                           \
+    if (tracer) {                                \
+      const unsigned long long now = clock64();  \
+      tr[j] += now - tr[4];                      \
+      tr[4] = now;                               \
+    }                                            \
   } while (0)
-  // B fragments: N column g of the MMA is batch row g; the columns 4..7 are padding -- their lanes simply re-read
-  // rows 0..3 (same addresses: a broadcast, no extra shared-memory traffic) and their results are never stored
-  const uint4* hb4 = reinterpret_cast<const uint4*>(&hbuf[g % RB][kh * NK1 * 16 + 4 * tq]);
-  const uint4* hrb4 = reinterpret_cast<const uint4*>(&hrbuf[g % RB][kq * NK2 * 16 + 4 * tq]);
-  const uint4* w2f = &w2frag[warp * NK2 * 2 * 32 + lane];
-  for (int s = 0; s < T; ++s, t += dt) {
-    const bool more = s + 1 < T;
-    if (tracer) tr[6] = clock64();
-    if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
-    if (tid == 0) {
-      mbar_arm(bar_h, FULL_BYTES);
-      mbar_arm(bar_hr, FULL_BYTES);
-    }
-    BG_STAMP(0);
-
-    // ---- phase 1: gate tile mt1, k-steps [kh * NK1, +NK1) ---------------------------------------
-    {
-      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < T; ++s) {
+      if (tracer) tr[4] = clock64();
+      if (s > 0) mbar_wait(bar_h, (uint32_t)((s - 1) & 1));
+      if (tid == EW_WARPS * 32) {
+        mbar_arm(bar_h, FULL_BYTES);    // arrivals of h'(s)
+        mbar_arm(bar_hr, FULL_BYTES);   // arrivals of (h*r)(s)
+      }
+      BG_STAMP(0);
+      {
+        float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < NK1; ++j) {
-        const uint4 v = hb4[j * 4];
-        mma_f16(c0, wg_head[j], v.x, v.z);
-        mma_f16(c1, wg_head[j], v.y, v.w);
-        mma_f16(c2, wg_tail[j], v.x, v.z);
-      }
-      if (tq < RB / 2) {
-        float* o = &red1[kh][2 * tq][mt1 * 16 + g];
-        o[0] = c0[0] + (c1[0] + c2[0]) * kTailUnscale;
-        o[RS1] = c0[1] + (c1[1] + c2[1]) * kTailUnscale;
-        o[8] = c0[2] + (c1[2] + c2[2]) * kTailUnscale;
-        o[RS1 + 8] = c0[3] + (c1[3] + c2[3]) * kTailUnscale;
-      }
-    }
-    BG_STAMP(1);
-    __syncthreads();
-    BG_STAMP(7);
-    if (gate_role) {
-      float sg[4] = {pg.x, pg.y, pg.z, pg.w};
+        for (int j = 0; j < NK1; ++j) {
+          const uint2 v = hb2[j * 4];
+          mma_f16(c1, wg_head[j], v.x, v.y);
+          mma_f16(c2, wg_tail[j], v.x, v.y);
+        }
+        // lanes tq < 2 hold rows 2 tq, 2 tq + 1 of head*head (c1) and tail*head (c2); head*tail of the same rows
+        // sits in c1 of lane + 2
 #pragma unroll
-      for (int k = 0; k < KS1; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(&red1[k][erow][goff + u_loc]);
-        sg[0] += x.x; sg[1] += x.y; sg[2] += x.z; sg[3] += x.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sg[i] = fast_sigmoid(sg[i]);
-      if (epi) {
-        uint32_t w0, w1, w2, w3;
-        split_pair(h_own[0] * sg[0], h_own[1] * sg[1], w0, w1);
-        split_pair(h_own[2] * sg[2], h_own[3] * sg[3], w2, w3);
-#pragma unroll
-        for (int p = 0; p < CS; ++p) st_async_v4_b32(map_to_rank(loc_hr, p), w0, w1, w2, w3, map_to_rank(bar_hr, p));
-      } else {
-        *reinterpret_cast<float4*>(&zbuf[erow][u_loc]) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-      }
-      if constexpr (TAPE) {
-        if (writer) *reinterpret_cast<float4*>(tape_ptr + gslot) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-      }
-      if (more && row_ok) pg = __ldg(reinterpret_cast<const float4*>(pre_ptr + pre_step + gslot));
-    }
-    BG_STAMP(2);
-
-    // ---- phase 2: candidate tile mt2, k-steps [kq * NK2, +NK2) ----------------------------------
-    mbar_wait(bar_hr, (uint32_t)(s & 1));
-    BG_STAMP(3);
-    {
-      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < NK2; ++j) {
-        const uint4 ah = w2f[(j * 2 + 0) * 32];
-        const uint4 at = w2f[(j * 2 + 1) * 32];
-        const uint32_t fh[4] = {ah.x, ah.y, ah.z, ah.w}, ft[4] = {at.x, at.y, at.z, at.w};
-        const uint4 v = hrb4[j * 4];
-        mma_f16(c0, fh, v.x, v.z);
-        mma_f16(c1, fh, v.y, v.w);
-        mma_f16(c2, ft, v.x, v.z);
-      }
-      if (tq < RB / 2) {
-        float* o = &red2[kq][2 * tq][mt2 * 16 + g];
-        o[0] = c0[0] + (c1[0] + c2[0]) * kTailUnscale;
-        o[RS2] = c0[1] + (c1[1] + c2[1]) * kTailUnscale;
-        o[8] = c0[2] + (c1[2] + c2[2]) * kTailUnscale;
-        o[RS2 + 8] = c0[3] + (c1[3] + c2[3]) * kTailUnscale;
-      }
-    }
-    BG_STAMP(4);
-    __syncthreads();
-    BG_STAMP(8);
-    if (epi) {
-      float sc[4] = {pa.x, pa.y, pa.z, pa.w};
-#pragma unroll
-      for (int k = 0; k < KS2; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(&red2[k][erow][u_loc]);
-        sc[0] += x.x; sc[1] += x.y; sc[2] += x.z; sc[3] += x.w;
-      }
-      const float4 z4 = *reinterpret_cast<const float4*>(&zbuf[erow][u_loc]);
-      const float zg[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sc[i] = fast_tanh(sc[i]);
-        float hn = sc[i] * zg[i] + h_own[i] * (1.f - zg[i]);
-        hn = pm * hn + (1.f - pm) * h_own[i];
-        h_own[i] = hn;
-      }
-      uint32_t w0, w1, w2, w3;
-      split_pair(h_own[0], h_own[1], w0, w1);
-      split_pair(h_own[2], h_own[3], w2, w3);
-      BG_STAMP(9);
-#pragma unroll
-      for (int p = 0; p < CS; ++p) st_async_v4_b32(map_to_rank(loc_h, p), w0, w1, w2, w3, map_to_rank(bar_h, p));
-      BG_STAMP(10);
-      if (writer) {
-        const float4 hv = make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
-        if (sub_phase == 0)
-          *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
-        if constexpr (TAPE) {
-          *reinterpret_cast<float4*>(tape_ptr) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-          *reinterpret_cast<float4*>(a.hext + ((long long)(t + 1) * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
+        for (int i = 0; i < 4; ++i) c1[i] += (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale;
+        if (tq < 2) {
+          out1[0] = c1[0];
+          out1[RS1] = c1[1];
+          out1[8] = c1[2];
+          out1[RS1 + 8] = c1[3];
         }
       }
+      named_bar_arrive(1, MMA_THREADS);
+      BG_STAMP(1);
+      mbar_wait(bar_hr, (uint32_t)(s & 1));
+      BG_STAMP(2);
+      {
+        float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NK2; ++j) {
+          const uint2 v = hrb2[j * 4];
+          mma_f16(c1, ws_head[j], v.x, v.y);
+          mma_f16(c2, ws_tail[j], v.x, v.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c1[i] += (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale;
+        if (tq < 2) {
+          out2[0] = c1[0];
+          out2[RS2] = c1[1];
+          out2[8] = c1[2];
+          out2[RS2 + 8] = c1[3];
+        }
+      }
+      named_bar_arrive(2, MMA_THREADS);
+      BG_STAMP(3);
     }
-    if (gate_role) {
-      pre_ptr += pre_step;
-      if constexpr (TAPE) tape_ptr += pre_step;
-      if (epi) {
+#undef BG_STAMP
+    // drain: the last h' copies must have landed everywhere before any CTA may exit
+    mbar_wait(bar_h, (uint32_t)((T - 1) & 1));
+    if (g_bigru_trace_on && tid == EW_WARPS * 32 && blockIdx.x < 1024) {
+      g_bigru_cta_cycles[0][blockIdx.x] = (unsigned long long)(t_loop - t_entry);
+      g_bigru_cta_cycles[1][blockIdx.x] = (unsigned long long)(clock64() - t_loop);
+    }
+  } else {
+    // =================================== elementwise warps ===========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(EW_REGS));
+    const bool active = tid < 2 * NROLE;
+    const bool lead = tid < NROLE;            // ships the heads, writes the outputs; the others ship the tails and own z
+    const int rid = tid % NROLE;
+    const int ug = rid % UG, erow = active ? rid / UG : 0;
+    const int u_loc = 4 * ug, u_glob = rank * UC + u_loc;
+    const bool row_ok = active && row0 + erow < B;
+    const bool writer = row_ok && lead;
+    const int plane = lead ? 0 : 1;
+    const uint32_t loc_h = smem_u32(&hbuf[plane][erow][u_glob / 2]), loc_hr = smem_u32(&hrbuf[plane][erow][u_glob / 2]);
+    float h_own[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h_own[i] = h0[u_glob + i];
+    if constexpr (TAPE) {
+      if (writer)
+        *reinterpret_cast<float4*>(a.hext + ((long long)(dir ? T + 1 : 0) * B + row0 + erow) * (2 * D) + dir * D + u_glob) =
+            make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
+    }
+    const long long pre_ld = 6LL * D;
+    const int dt = dir ? -1 : 1;
+    int t = dir ? (T - 1) : 0;
+    // fork pre-activations of this thread's 4 units: [inputs | update | reset]; every slot is re-loaded for the next step
+    // right after its consumer, so a load has most of a step to land and nothing is double-buffered
+    const long long pre_off = ((long long)t * B + row0 + erow) * pre_ld + (long long)dir * 3 * D + u_glob;
+    const float* pre_ptr = a.pre + pre_off;
+    float* tape_ptr = TAPE ? a.tape + pre_off : nullptr;
+    const float* pm_ptr = a.mask ? a.mask + (long long)t * a.mask_tstride + row0 + erow : nullptr;
+    const long long pre_step = (long long)dt * B * pre_ld, mask_step = (long long)dt * a.mask_tstride;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pa = zero4, pz = zero4, pr = zero4;
+    float pm = 1.f;
+    if (row_ok) {
+      pa = __ldg(reinterpret_cast<const float4*>(pre_ptr));
+      if (!lead) pz = __ldg(reinterpret_cast<const float4*>(pre_ptr + D));
+      pr = __ldg(reinterpret_cast<const float4*>(pre_ptr + 2 * D));
+      if (pm_ptr) pm = __ldg(pm_ptr);
+    }
+    int sub_phase = dir ? ((T - 1) % a.subsample) : 0;   // t % subsample, maintained incrementally
+    int t_out = t / a.subsample;
+    const bool tracer = tracing && tid == 0;
+#define BG_STAMP(j)                              \
+  do {                                           \
+    if (tracer) {                                \
+      const unsigned long long now = clock64();  \
+      tr[j] += now - tr[5];                      \
+      tr[5] = now;                               \
+    }                                            \
+  } while (0)
+    for (int s = 0; s < T; ++s, t += dt) {
+      const bool more = s + 1 < T;
+      if (tracer) tr[5] = clock64();
+      named_bar_sync(1, MMA_THREADS);
+      BG_STAMP(6);
+      if (active) {
+        float sr[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+        for (int k = 0; k < KS1; ++k) {
+          const float4 x = *reinterpret_cast<const float4*>(&red1[k][erow][UC + u_loc]);
+          sr[0] += x.x; sr[1] += x.y; sr[2] += x.z; sr[3] += x.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sr[i] = fast_sigmoid(sr[i]);
+        uint32_t w0, w1, w2, w3;
+        split_pair(h_own[0] * sr[0], h_own[1] * sr[1], w0, w1);
+        split_pair(h_own[2] * sr[2], h_own[3] * sr[3], w2, w3);
+        const uint32_t x0 = lead ? w0 : w1, x1 = lead ? w2 : w3;
+#pragma unroll
+        for (int p = 0; p < CS; ++p) st_async_v2_b32(map_to_rank(loc_hr, p), x0, x1, map_to_rank(bar_hr, p));
+        if constexpr (TAPE) {
+          if (writer) *reinterpret_cast<float4*>(tape_ptr + 2 * D) = make_float4(sr[0], sr[1], sr[2], sr[3]);
+        }
+        if (more && row_ok) pr = __ldg(reinterpret_cast<const float4*>(pre_ptr + pre_step + 2 * D));
+        if (!lead) {
+          float sz[4] = {pz.x, pz.y, pz.z, pz.w};
+#pragma unroll
+          for (int k = 0; k < KS1; ++k) {
+            const float4 x = *reinterpret_cast<const float4*>(&red1[k][erow][u_loc]);
+            sz[0] += x.x; sz[1] += x.y; sz[2] += x.z; sz[3] += x.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sz[i] = fast_sigmoid(sz[i]);
+          *reinterpret_cast<float4*>(&zbuf[erow][u_loc]) = make_float4(sz[0], sz[1], sz[2], sz[3]);
+          if constexpr (TAPE) {
+            if (row_ok) *reinterpret_cast<float4*>(tape_ptr + D) = make_float4(sz[0], sz[1], sz[2], sz[3]);
+          }
+          if (more && row_ok) pz = __ldg(reinterpret_cast<const float4*>(pre_ptr + pre_step + D));
+        }
+      }
+      BG_STAMP(7);
+      named_bar_sync(2, MMA_THREADS);
+      BG_STAMP(8);
+      if (active) {
+        float sc[4] = {pa.x, pa.y, pa.z, pa.w};
+#pragma unroll
+        for (int k = 0; k < KS2; ++k) {
+          const float4 x = *reinterpret_cast<const float4*>(&red2[k][erow][u_loc]);
+          sc[0] += x.x; sc[1] += x.y; sc[2] += x.z; sc[3] += x.w;
+        }
+        const float4 z4 = *reinterpret_cast<const float4*>(&zbuf[erow][u_loc]);
+        const float zg[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          sc[i] = fast_tanh(sc[i]);
+          float hn = sc[i] * zg[i] + h_own[i] * (1.f - zg[i]);
+          hn = pm * hn + (1.f - pm) * h_own[i];
+          h_own[i] = hn;
+        }
+        uint32_t w0, w1, w2, w3;
+        split_pair(h_own[0], h_own[1], w0, w1);
+        split_pair(h_own[2], h_own[3], w2, w3);
+        const uint32_t x0 = lead ? w0 : w1, x1 = lead ? w2 : w3;
+#pragma unroll
+        for (int p = 0; p < CS; ++p) st_async_v2_b32(map_to_rank(loc_h, p), x0, x1, map_to_rank(bar_h, p));
+        if (writer) {
+          const float4 hv = make_float4(h_own[0], h_own[1], h_own[2], h_own[3]);
+          if (sub_phase == 0)
+            *reinterpret_cast<float4*>(a.out + ((long long)t_out * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
+          if constexpr (TAPE) {
+            *reinterpret_cast<float4*>(tape_ptr) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+            *reinterpret_cast<float4*>(a.hext + ((long long)(t + 1) * B + row0 + erow) * (2 * D) + dir * D + u_glob) = hv;
+          }
+        }
+        pre_ptr += pre_step;
+        if constexpr (TAPE) tape_ptr += pre_step;
         if (pm_ptr) pm_ptr += mask_step;
         if (more && row_ok) {
           pa = __ldg(reinterpret_cast<const float4*>(pre_ptr));
           if (pm_ptr) pm = __ldg(pm_ptr);
         }
       }
+      BG_STAMP(9);
+      // advance t % subsample and t / subsample without dividing
+      if (dir == 0) {
+        if (++sub_phase == a.subsample) { sub_phase = 0; ++t_out; }
+      } else {
+        if (sub_phase == 0) { sub_phase = a.subsample - 1; --t_out; } else { --sub_phase; }
+      }
     }
-    BG_STAMP(5);
-    if (dir == 0) {
-      if (++sub_phase == a.subsample) { sub_phase = 0; ++t_out; }
-    } else {
-      if (sub_phase == 0) { sub_phase = a.subsample - 1; --t_out; } else { --sub_phase; }
-    }
-  }
 #undef BG_STAMP
-  if (g_bigru_trace_on && tid == 32 && blockIdx.x < 1024) {   // a thread without an elementwise role
-    g_bigru_cta_cycles[0][blockIdx.x] = (unsigned long long)(t_loop - t_entry);
-    g_bigru_cta_cycles[1][blockIdx.x] = (unsigned long long)(clock64() - t_loop);
   }
-  if (tracer) {
+  __syncthreads();
+  if (tracing && tid == 0) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) g_bigru_trace[j] = tr[j];
-    g_bigru_trace[6] = (unsigned long long)T;
-    g_bigru_trace[7] = tr[7];
-    g_bigru_trace[8] = tr[8];
-    g_bigru_trace[9] = tr[9];
-    g_bigru_trace[10] = tr[10];
+    for (int j = 0; j < 4; ++j) g_bigru_trace[j] = tr[j];
+#pragma unroll
+    for (int j = 6; j < 10; ++j) g_bigru_trace[j - 2] = tr[j];
+    g_bigru_trace[8] = (unsigned long long)T;
   }
-  mbar_wait(bar_h, (uint32_t)((T - 1) & 1));
   cluster_sync_all();
 }
 
@@ -782,17 +808,10 @@ int launch_bigru(const BiGruArgs& a, cudaStream_t stream) {
 
 template <int D, bool TAPE>
 int mma_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int clusters, cudaStream_t stream) {
-  static bool configured[LVSR_MAX_DEVICES] = {false};
-  const int dev = current_device();
-  if (!configured[dev]) {
-    LVSR_CUDA_OK(cudaFuncSetAttribute(bigru_mma_kernel<D, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)bigru_mma_dyn_smem<D>()));
-    configured[dev] = true;
-  }
   cfg = {};
   cfg.gridDim = dim3(MMA_CS * clusters);
-  cfg.blockDim = dim3(MMA_NWARP * 32);
-  cfg.dynamicSmemBytes = bigru_mma_dyn_smem<D>();
+  cfg.blockDim = dim3(MMA_THREADS);
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = MMA_CS;
@@ -819,11 +838,11 @@ int launch_bigru_mma_t(const BiGruArgs& a, cudaStream_t stream) {
     unsigned long long h[12] = {0};
     LVSR_CUDA_OK(cudaMemcpyFromSymbolAsync(h, g_bigru_trace, sizeof(h), 0, cudaMemcpyDeviceToHost, stream));
     LVSR_CUDA_OK(cudaStreamSynchronize(stream));
-    const double n = h[6] ? (double)h[6] : 1.0;
+    const double n = h[8] ? (double)h[8] : 1.0;
     fprintf(stderr,
-            "[bigru trace] mma<%d> T=%llu cycles/step: wait_h=%.0f gates=%.0f barrier=%.0f gate_epi+send=%.0f wait_hr=%.0f "
-            "cand=%.0f barrier=%.0f cand_math=%.0f sends=%.0f stores+prefetch=%.0f\n",
-            D, h[6], h[0] / n, h[1] / n, h[7] / n, h[2] / n, h[3] / n, h[4] / n, h[8] / n, h[9] / n, h[10] / n, h[5] / n);
+            "[bigru trace] mma<%d> T=%llu cycles/step  MMA warp: wait_h=%.0f gates=%.0f wait_hr=%.0f cand=%.0f | elementwise: "
+            "wait_gates=%.0f r+send(+z)=%.0f wait_cand=%.0f cand+send+stores=%.0f\n",
+            D, h[8], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n);
     static unsigned long long cc[2][1024];
     LVSR_CUDA_OK(cudaMemcpyFromSymbol(cc, g_bigru_cta_cycles, sizeof(cc)));
     const int nc = (int)cfg.gridDim.x < 1024 ? (int)cfg.gridDim.x : 1024;
