@@ -477,6 +477,22 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
 
+// the two non-linearities of the elementwise warps, on the flush-to-zero forms of ex2 / rcp: the default approx forms wrap
+// every MUFU in a subnormal range fix-up (two more dependent instructions on the critical chain of a step); a flushed
+// exp only matters beyond |x| ~ 87, where the gate is 0 / 1 to 1e-38 either way
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_ftz(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_ftz(float x) { return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)); }
+
 constexpr int MMA_CS = 4, MMA_WARPS = 8, EW_WARPS = 4, MMA_THREADS = (MMA_WARPS + EW_WARPS) * 32;
 // setmaxnreg redistributes the registers the CTA was LAUNCHED with (384 threads x 168), not the SM's whole file:
 // 256 * 224 + 128 * 56 = 64512 = 384 * 168
@@ -496,6 +512,7 @@ bigru_mma_kernel(BiGruArgs a) {
   constexpr int UG = UC / 4;            // 4-unit groups of this CTA
   constexpr int NROLE = RB * UG;        // (row, unit group) roles
   static_assert(MT1 * KS1 == MMA_WARPS && MT2 * KS2 == MMA_WARPS && NK1 * KS1 == NK && NK2 * KS2 == NK, "tile split");
+  static_assert(NK1 % 2 == 0 && NK2 % 2 == 0, "two k-steps per round of the MMA loops");
   static_assert(2 * NROLE <= EW_WARPS * 32, "elementwise roles");
   static_assert(RB == 4, "N columns: 4 rows of heads + 4 rows of tails");
   // a plane row: 2 words per 4-unit group = packed (u, u+1), (u+2, u+3); + 8 words: the 16 lanes of a load phase
@@ -598,12 +615,22 @@ bigru_mma_kernel(BiGruArgs a) {
       }
       BG_STAMP(0);
       {
+        // four accumulation chains per warp (even / odd k-steps x head / tail weights): with two warps per scheduler a
+        // chain of dependent MMAs would otherwise leave the tensor pipe waiting for its own results
         float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < NK1; ++j) {
-          const uint2 v = hb2[j * 4];
+        for (int j = 0; j < NK1; j += 2) {
+          const uint2 v = hb2[j * 4], w = hb2[j * 4 + 4];
           mma_f16(c1, wg_head[j], v.x, v.y);
           mma_f16(c2, wg_tail[j], v.x, v.y);
+          mma_f16(d1, wg_head[j + 1], w.x, w.y);
+          mma_f16(d2, wg_tail[j + 1], w.x, w.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c1[i] += d1[i];
+          c2[i] += d2[i];
         }
         // lanes tq < 2 hold rows 2 tq, 2 tq + 1 of head*head (c1) and tail*head (c2); head*tail of the same rows
         // sits in c1 of lane + 2
@@ -622,11 +649,19 @@ bigru_mma_kernel(BiGruArgs a) {
       BG_STAMP(2);
       {
         float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < NK2; ++j) {
-          const uint2 v = hrb2[j * 4];
+        for (int j = 0; j < NK2; j += 2) {
+          const uint2 v = hrb2[j * 4], w = hrb2[j * 4 + 4];
           mma_f16(c1, ws_head[j], v.x, v.y);
           mma_f16(c2, ws_tail[j], v.x, v.y);
+          mma_f16(d1, ws_head[j + 1], w.x, w.y);
+          mma_f16(d2, ws_tail[j + 1], w.x, w.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          c1[i] += d1[i];
+          c2[i] += d2[i];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) c1[i] += (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale;
@@ -710,7 +745,7 @@ bigru_mma_kernel(BiGruArgs a) {
           sr[0] += x.x; sr[1] += x.y; sr[2] += x.z; sr[3] += x.w;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sr[i] = fast_sigmoid(sr[i]);
+        for (int i = 0; i < 4; ++i) sr[i] = sigmoid_ftz(sr[i]);
         uint32_t w0, w1, w2, w3;
         split_pair(h_own[0] * sr[0], h_own[1] * sr[1], w0, w1);
         split_pair(h_own[2] * sr[2], h_own[3] * sr[3], w2, w3);
@@ -729,7 +764,7 @@ bigru_mma_kernel(BiGruArgs a) {
             sz[0] += x.x; sz[1] += x.y; sz[2] += x.z; sz[3] += x.w;
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) sz[i] = fast_sigmoid(sz[i]);
+          for (int i = 0; i < 4; ++i) sz[i] = sigmoid_ftz(sz[i]);
           *reinterpret_cast<float4*>(&zbuf[erow][u_loc]) = make_float4(sz[0], sz[1], sz[2], sz[3]);
           if constexpr (TAPE) {
             if (row_ok) *reinterpret_cast<float4*>(tape_ptr + D) = make_float4(sz[0], sz[1], sz[2], sz[3]);
@@ -751,7 +786,7 @@ bigru_mma_kernel(BiGruArgs a) {
         const float zg[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          sc[i] = fast_tanh(sc[i]);
+          sc[i] = tanh_ftz(sc[i]);
           float hn = sc[i] * zg[i] + h_own[i] * (1.f - zg[i]);
           hn = pm * hn + (1.f - pm) * h_own[i];
           h_own[i] = hn;

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd /root/repo
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_metric.py tests/test_gpu_train.py -x -q 2>&1 | tail -3
+for v in old new old new; do
+  if [ $v = old ]; then export LVSR_B200_LIB=$PWD/tools/ab/liblvsr_old.so; else unset LVSR_B200_LIB; fi
+  timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-train 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', round(d['value']), d['ms_per_step'], d['kernel_ms_per_step']['bigru'])"
+done
+unset LVSR_B200_LIB
+LVSR_BIGRU_TRACE=1 timeout 200 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train 2>&1 | grep "bigru trace" | tail -4
+timeout 300 python bench.py --mode train --steps 3 --warmup 2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('train', d['ms_per_step'], json.dumps(d['kernel_ms_per_step']))"
