@@ -498,6 +498,20 @@ constexpr int MMA_CS = 4, MMA_WARPS = 8, EW_WARPS = 4, MMA_THREADS = (MMA_WARPS 
 // 256 * 224 + 128 * 56 = 64512 = 384 * 168
 constexpr int MMA_REGS = 224, EW_REGS = 56;
 
+// Largest magnitude among the weights one warp turns into A fragments -> power-of-two scale that keeps the fp16 heads
+// far inside the fp16 range (|w| * scale <= 2^14); the warp multiplies its partial sums by the inverse.  Parameters of
+// any magnitude therefore give the same result as the fp32 kernel (1.0 / 1.0 for every sane model: an exact no-op).
+__device__ __forceinline__ float range_scale(float warp_max_abs, float& inverse) {
+  float scale = 1.f;
+  inverse = 1.f;
+  if (warp_max_abs > 16384.f && warp_max_abs < 3.0e38f) {
+    const int e = ((__float_as_int(warp_max_abs) >> 23) & 0xff) - 127;   // 2^e <= max < 2^(e+1)
+    scale = __int_as_float((127 - (e - 13)) << 23);                      // 2^-(e-13)
+    inverse = __int_as_float((127 + (e - 13)) << 23);
+  }
+  return scale;
+}
+
 template <int D, bool TAPE>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 bigru_mma_kernel(BiGruArgs a) {
@@ -568,28 +582,58 @@ bigru_mma_kernel(BiGruArgs a) {
     // ---- weights -> A fragments (once).  MMA k index kk of k-step ks <-> unit 16 ks + 4 (kk/2 % 4) + 2 (kk / 8) + kk % 2:
     // lane tq then needs the packed pairs of the four consecutive units 16 ks + 4 tq .. + 3 of a row = 8 bytes of a plane
     uint32_t wg_head[NK1][4], wg_tail[NK1][4], ws_head[NK2][4], ws_tail[NK2][4];
+    float inv_g, inv_s;   // see range_scale()
+    {
+      float mx = 0.f;
 #pragma unroll
-    for (int j = 0; j < NK1; ++j) {
-      const int k0 = (kh * NK1 + j) * 16 + 4 * tq;
+      for (int j = 0; j < NK1; ++j)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
-        const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
-        split_pair(Wg[(long long)k0 * (2 * D) + col], Wg[(long long)(k0 + 1) * (2 * D) + col], wg_head[j][half],
-                   wg_tail[j][half]);
-        split_pair(Wg[(long long)(k0 + 2) * (2 * D) + col], Wg[(long long)(k0 + 3) * (2 * D) + col], wg_head[j][2 + half],
-                   wg_tail[j][2 + half]);
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
+            const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
+            mx = fmaxf(mx, fabsf(Wg[(long long)((kh * NK1 + j) * 16 + 4 * tq + kk) * (2 * D) + col]));
+          }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float sc = range_scale(mx, inv_g);
+#pragma unroll
+      for (int j = 0; j < NK1; ++j) {
+        const int k0 = (kh * NK1 + j) * 16 + 4 * tq;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int ul = 16 * (mt1 % (MT1 / 2)) + g + 8 * half;
+          const long long col = (mt1 < MT1 / 2 ? 0 : D) + rank * UC + ul;
+          split_pair(sc * Wg[(long long)k0 * (2 * D) + col], sc * Wg[(long long)(k0 + 1) * (2 * D) + col], wg_head[j][half],
+                     wg_tail[j][half]);
+          split_pair(sc * Wg[(long long)(k0 + 2) * (2 * D) + col], sc * Wg[(long long)(k0 + 3) * (2 * D) + col],
+                     wg_head[j][2 + half], wg_tail[j][2 + half]);
+        }
       }
     }
+    {
+      float mx = 0.f;
 #pragma unroll
-    for (int j = 0; j < NK2; ++j) {
-      const int k0 = (kq * NK2 + j) * 16 + 4 * tq;
+      for (int j = 0; j < NK2; ++j)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const long long col = rank * UC + 16 * mt2 + g + 8 * half;
-        split_pair(Ws[(long long)k0 * D + col], Ws[(long long)(k0 + 1) * D + col], ws_head[j][half], ws_tail[j][half]);
-        split_pair(Ws[(long long)(k0 + 2) * D + col], Ws[(long long)(k0 + 3) * D + col], ws_head[j][2 + half],
-                   ws_tail[j][2 + half]);
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mx = fmaxf(mx, fabsf(Ws[(long long)((kq * NK2 + j) * 16 + 4 * tq + kk) * D + rank * UC + 16 * mt2 + g + 8 * half]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float sc = range_scale(mx, inv_s);
+#pragma unroll
+      for (int j = 0; j < NK2; ++j) {
+        const int k0 = (kq * NK2 + j) * 16 + 4 * tq;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const long long col = rank * UC + 16 * mt2 + g + 8 * half;
+          split_pair(sc * Ws[(long long)k0 * D + col], sc * Ws[(long long)(k0 + 1) * D + col], ws_head[j][half], ws_tail[j][half]);
+          split_pair(sc * Ws[(long long)(k0 + 2) * D + col], sc * Ws[(long long)(k0 + 3) * D + col], ws_head[j][2 + half],
+                     ws_tail[j][2 + half]);
+        }
       }
     }
     // B fragments: N column g < 4 = heads of batch row g, N column g >= 4 = tails of batch row g - 4
@@ -635,7 +679,7 @@ bigru_mma_kernel(BiGruArgs a) {
         // lanes tq < 2 hold rows 2 tq, 2 tq + 1 of head*head (c1) and tail*head (c2); head*tail of the same rows
         // sits in c1 of lane + 2
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c1[i] += (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale;
+        for (int i = 0; i < 4; ++i) c1[i] = (c1[i] + (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale) * inv_g;
         if (tq < 2) {
           out1[0] = c1[0];
           out1[RS1] = c1[1];
@@ -664,7 +708,7 @@ bigru_mma_kernel(BiGruArgs a) {
           c2[i] += d2[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c1[i] += (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale;
+        for (int i = 0; i < 4; ++i) c1[i] = (c1[i] + (__shfl_down_sync(0xffffffffu, c1[i], 2) + c2[i]) * kTailUnscale) * inv_s;
         if (tq < 2) {
           out2[0] = c1[0];
           out2[RS2] = c1[1];

@@ -188,3 +188,55 @@ def test_model_on_second_device_while_first_is_current():
         att, attm = rec.encode(x, m)
         assert str(att.device) == dev
         assert rel_err(rec.cost_matrix(labels, lm, att, attm).cpu().numpy(), want) < 1e-4
+
+
+# ---- the tensor-core BiGRU kernel (hidden size 256: bigru_mma_kernel in csrc/bigru.cu) -------------------------------
+ENC256 = dict(PYRAMID, dims_bidir=[256, 256], subsample=[1, 2])
+WSJ_ENC = dict(PYRAMID, dims_bidir=[256, 256, 256, 256], subsample=[1, 1, 2, 2])
+
+
+@pytest.mark.parametrize("B,T", [(1, 9), (3, 8), (5, 33), (33, 21)])
+def test_tensor_core_bigru_odd_shapes(B, T):
+    """The mma.sync BiGRU kernel on batches that do not fill its 4-row clusters, that need 18 clusters (33 rows) and on
+    lengths that are not multiples of the subsampling; ragged masks.  Same oracle bar as every other path."""
+    _torch()
+    cfg = O.make_config(**ENC256)
+    params = O.init_params(cfg, seed=4, scale=10.0)
+    x, m, labels, lm = O.synthetic_batch(cfg, B=B, T=T, seed=B * 10 + T, min_frac=0.2)
+    if B >= 3:
+        m[:, 0] = (np.arange(T) < 1)          # a one-frame utterance
+        x *= m[:, :, None]
+    _compare_cost(cfg, params, x, m, labels, lm)
+
+
+def test_tensor_core_bigru_agrees_with_the_fp32_kernel(monkeypatch):
+    """fp16 head/tail operands must reproduce the FFMA kernel to fp32 round-off at the metric batch (the split drops
+    terms of 2^-22 only): run both kernels of csrc/bigru.cu on the same input."""
+    torch = _torch()
+    cfg = O.make_config(**WSJ_ENC)
+    params = O.init_params(cfg, seed=9, scale=10.0)
+    x, m, _, _ = O.synthetic_batch(cfg, B=64, T=200, seed=77, dtype=np.float32)
+    rec = make_recognizer(cfg, params)
+    monkeypatch.setenv("LVSR_BIGRU_MMA", "0")
+    ref = rec.encode(x, m)[0].clone()
+    monkeypatch.setenv("LVSR_BIGRU_MMA", "1")
+    got = rec.encode(x, m)[0]
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print("mma vs ffma bigru", err)
+    assert bool(torch.isfinite(got).all()) and err < 1e-5
+
+
+def test_recurrent_weights_beyond_the_fp16_range():
+    """A recurrent weight of 1e5 (fp16 overflows at 65504): the tensor-core kernel rescales a tile's fragments by a power
+    of two, so the result is the fp32 kernel's -- the unit saturates, everything else keeps its accuracy."""
+    _torch()
+    cfg = O.make_config(**ENC256)
+    params = O.init_params(cfg, seed=6, scale=10.0)
+    for name in sorted(params):
+        if name.endswith("gatedrecurrent.state_to_state") or name.endswith("gatedrecurrent.state_to_gates"):
+            w = np.array(params[name])
+            w[3, 5] = 1.0e5
+            w[17, w.shape[1] - 2] = -2.5e5
+            params[name] = w
+    x, m, labels, lm = O.synthetic_batch(cfg, B=4, T=24, seed=21)
+    _compare_cost(cfg, params, x, m, labels, lm)
