@@ -24,7 +24,9 @@
 // History (profiles/): r1a 4-byte remote stores + barrier.cluster (30 % of the kernel in the fence, 8.6 us/step)
 // -> bulk DSMEM copies + mbarrier (3.07 us) -> k over 8 lanes, FFMA2 (2.76 us) -> k over 16 lanes, 4 CTAs x 16 warps,
 // st.async from registers (2.34 us in the loop, 2.67 us/step with launch and staging): the products are bound by the
-// shared-memory return path of the h loads, the rest is lock-step latency (profiles/r1g_summary.md).
+// shared-memory return path of the h loads, the rest is lock-step latency (profiles/r1g_summary.md)
+// -> round 2: hidden size 256 runs bigru_mma_kernel below (mma.sync on fp16 head/tail splits, weights as the M dimension,
+// warp-specialised): 1.40 us per step (profiles/r2i_summary.md); the FFMA kernel stays for the other hidden sizes.
 #include <cuda_fp16.h>
 
 #include "kernels.h"
@@ -1016,8 +1018,10 @@ int bigru_layer(const BiGruArgs& a, cudaStream_t stream) {
   const int groups = ceil_div(a.B, RB);
   bool wide = a.D == 256 && 8 * groups * 2 > bigru_sm_count() && groups * 2 <= wide_clusters_resident();
   if (const char* e = getenv("LVSR_BIGRU_WIDE")) wide = a.D == 256 && atoi(e) != 0;
-  // tensor-core products whenever every cluster gets four SMs of its own (otherwise the launch runs in waves)
-  bool mma = a.D == 256 && groups * 2 <= mma_clusters_resident<256>();
+  // hidden size 256: tensor-core products.  Clusters never talk to each other, so a batch with more clusters than the
+  // device holds at once (mma_clusters_resident: 33 on a B200, i.e. more than 66 rows) simply runs in waves -- still
+  // ahead of the FFMA kernels, which would have to put two or more CTAs on every SM for such a batch.
+  bool mma = a.D == 256 && mma_clusters_resident<256>() > 0;
   if (const char* e = getenv("LVSR_BIGRU_MMA")) mma = a.D == 256 && atoi(e) != 0;
   if (mma) return launch_bigru_mma<256>(a, stream);
   switch (a.D) {

@@ -661,9 +661,13 @@ def main():
         t_l = -(-t_l // k)
     D = NET["dims_bidir"][0]
     fma_per_step = 2 * W["B"] * 3 * D * D
-    recurrence = {"kernel": "bigru_kernel", "sequential_steps": enc_steps,
+    # D = 256: bigru_mma_kernel -- mma.sync m16n8k16 on fp16 head/tail splits (fp32-equivalent);
+    # per CTA and step 12 weight tiles x 16 k-steps x 2 MMAs at the measured 2.0 cycles per MMA and SM
+    # (tools/micro/mma_rate.cu) = 768 cycles of tensor pipe
+    recurrence = {"kernel": "bigru_mma_kernel" if D == 256 else "bigru_kernel", "sequential_steps": enc_steps,
                   "us_per_step": prof["bigru"]["ms"] * 1e3 / enc_steps if enc_steps else None,
-                  "fp32_fma_floor_us": fma_per_step / (148 * 128 * 1.965e9) * 1e6}
+                  "fp32_fma_floor_us": fma_per_step / (148 * 128 * 1.965e9) * 1e6,
+                  "mma_sync_floor_us": (12 * (D // 16) * 2 * 2.0) / 1.965e9 * 1e6 if D == 256 else None}
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

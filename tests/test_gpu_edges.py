@@ -195,10 +195,11 @@ ENC256 = dict(PYRAMID, dims_bidir=[256, 256], subsample=[1, 2])
 WSJ_ENC = dict(PYRAMID, dims_bidir=[256, 256, 256, 256], subsample=[1, 1, 2, 2])
 
 
-@pytest.mark.parametrize("B,T", [(1, 9), (3, 8), (5, 33), (33, 21)])
+@pytest.mark.parametrize("B,T", [(1, 9), (3, 8), (5, 33), (33, 21), (70, 12)])
 def test_tensor_core_bigru_odd_shapes(B, T):
-    """The mma.sync BiGRU kernel on batches that do not fill its 4-row clusters, that need 18 clusters (33 rows) and on
-    lengths that are not multiples of the subsampling; ragged masks.  Same oracle bar as every other path."""
+    """The mma.sync BiGRU kernel on batches that do not fill its 4-row clusters, that need 18 clusters (33 rows) or more
+    clusters than the device holds at once (70 rows -> 36 clusters, two waves) and on lengths that are not multiples of
+    the subsampling; ragged masks.  Same oracle bar as every other path."""
     _torch()
     cfg = O.make_config(**ENC256)
     params = O.init_params(cfg, seed=4, scale=10.0)
