@@ -479,22 +479,6 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
 
-// the two non-linearities of the elementwise warps, on the flush-to-zero forms of ex2 / rcp: the default approx forms wrap
-// every MUFU in a subnormal range fix-up (two more dependent instructions on the critical chain of a step); a flushed
-// exp only matters beyond |x| ~ 87, where the gate is 0 / 1 to 1e-38 either way
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_ftz(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_ftz(float x) { return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)); }
-
 constexpr int MMA_CS = 4, MMA_WARPS = 8, EW_WARPS = 4, MMA_THREADS = (MMA_WARPS + EW_WARPS) * 32;
 // setmaxnreg redistributes the registers the CTA was LAUNCHED with (384 threads x 168), not the SM's whole file:
 // 256 * 224 + 128 * 56 = 64512 = 384 * 168
@@ -791,7 +775,7 @@ bigru_mma_kernel(BiGruArgs a) {
           sr[0] += x.x; sr[1] += x.y; sr[2] += x.z; sr[3] += x.w;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sr[i] = sigmoid_ftz(sr[i]);
+        for (int i = 0; i < 4; ++i) sr[i] = fast_sigmoid(sr[i]);
         uint32_t w0, w1, w2, w3;
         split_pair(h_own[0] * sr[0], h_own[1] * sr[1], w0, w1);
         split_pair(h_own[2] * sr[2], h_own[3] * sr[3], w2, w3);
@@ -810,7 +794,7 @@ bigru_mma_kernel(BiGruArgs a) {
             sz[0] += x.x; sz[1] += x.y; sz[2] += x.z; sz[3] += x.w;
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) sz[i] = sigmoid_ftz(sz[i]);
+          for (int i = 0; i < 4; ++i) sz[i] = fast_sigmoid(sz[i]);
           *reinterpret_cast<float4*>(&zbuf[erow][u_loc]) = make_float4(sz[0], sz[1], sz[2], sz[3]);
           if constexpr (TAPE) {
             if (row_ok) *reinterpret_cast<float4*>(tape_ptr + D) = make_float4(sz[0], sz[1], sz[2], sz[3]);
@@ -832,7 +816,7 @@ bigru_mma_kernel(BiGruArgs a) {
         const float zg[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          sc[i] = tanh_ftz(sc[i]);
+          sc[i] = fast_tanh(sc[i]);
           float hn = sc[i] * zg[i] + h_own[i] * (1.f - zg[i]);
           hn = pm * hn + (1.f - pm) * h_own[i];
           h_own[i] = hn;
