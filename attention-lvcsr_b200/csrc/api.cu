@@ -324,6 +324,12 @@ int lvsr_model_destroy(lvsr_model* m) {
   for (float* p : m->bcat) if (p) cudaFree(p);
   for (float* p : m->Wcat_hi) if (p) cudaFree(p);
   for (float* p : m->Wcat_lo) if (p) cudaFree(p);
+  for (void* p : m->Wcat_h16_head) if (p) cudaFree(p);
+  for (void* p : m->Wcat_h16_tail) if (p) cudaFree(p);
+  for (float* p : m->Wcat_h16_scale) if (p) cudaFree(p);
+  if (m->Wp_h16_head) cudaFree(m->Wp_h16_head);
+  if (m->Wp_h16_tail) cudaFree(m->Wp_h16_tail);
+  if (m->Wp_h16_scale) cudaFree(m->Wp_h16_scale);
   if (m->Wp_hi) cudaFree(m->Wp_hi);
   if (m->Wp_lo) cudaFree(m->Wp_lo);
   if (m->Wd_cat) cudaFree(m->Wd_cat);
@@ -404,6 +410,53 @@ int lvsr_model_finalize(lvsr_model* m) {
 }  // extern "C"
 
 namespace lvsr {
+// fp16 head/tail operands for the projections that read BiGRU outputs (|h| <= 1): layers >= 1 and preprocess.
+// Allocated and split at their first use after a parameter change, i.e. AFTER the caller has reserved the workspace arena:
+// the arena keeps the device pages it gets without these buffers (the persistent decoder's step time moves by up to 10 %
+// with the physical placement of its buffers, profiles/r2k_summary.md).
+int ensure_h16(lvsr_model* m, cudaStream_t st) {
+  if (!m->use_tc || !m->use_h16 || !m->h16_stale) return 0;
+  const lvsr_config& c = m->cfg;
+  if (m->Wcat_h16_head.empty()) {
+    int dk2 = c.num_features;
+    for (int l = 0; l < c.num_layers; ++l) {
+      const int D = c.dims_bidir[l];
+      void *h = nullptr, *t = nullptr;
+      float* sc = nullptr;
+      if (l >= 1 && gemm_tc_h16_supported(128, 6 * D, dk2)) {
+        const size_t bytes = (size_t)gemm_tc_kpad_h16(dk2) * 6 * D * 2;
+        LVSR_CUDA_OK(cudaMalloc(&h, bytes));
+        LVSR_CUDA_OK(cudaMalloc(&t, bytes));
+        LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sc), 2 * sizeof(float)));
+      }
+      m->Wcat_h16_head.push_back(h);
+      m->Wcat_h16_tail.push_back(t);
+      m->Wcat_h16_scale.push_back(sc);
+      dk2 = 2 * D;
+    }
+    if (gemm_tc_h16_supported(128, c.dim_matcher, m->E)) {
+      const size_t bytes = (size_t)gemm_tc_kpad_h16(m->E) * c.dim_matcher * 2;
+      LVSR_CUDA_OK(cudaMalloc(&m->Wp_h16_head, bytes));
+      LVSR_CUDA_OK(cudaMalloc(&m->Wp_h16_tail, bytes));
+      LVSR_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->Wp_h16_scale), 2 * sizeof(float)));
+    }
+  }
+  int dk2 = c.num_features;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int D = c.dims_bidir[l];
+    if (m->Wcat_h16_head[l])
+      if (int rc = split_weight_h16(m->Wcat[l], dk2, 6 * D, m->Wcat_h16_head[l], m->Wcat_h16_tail[l], m->Wcat_h16_scale[l], st))
+        return rc;
+    dk2 = 2 * D;
+  }
+  if (m->Wp_h16_head)
+    if (int rc = split_weight_h16(m->P(std::string(ATT) + "/preprocess.W"), m->E, c.dim_matcher, m->Wp_h16_head, m->Wp_h16_tail,
+                                  m->Wp_h16_scale, st))
+      return rc;
+  m->h16_stale = false;
+  return 0;
+}
+
 int finalize_on_stream(lvsr_model* m, cudaStream_t st, bool synchronise) {
   const lvsr_config& c = m->cfg;
   if (m->Wcat.empty()) {
@@ -480,6 +533,12 @@ int finalize_on_stream(lvsr_model* m, cudaStream_t st, bool synchronise) {
     if (m->Wp_hi)
       if (int rc = split_weight_tf32(m->P(std::string(ATT) + "/preprocess.W"), m->E, c.dim_matcher, m->Wp_hi, m->Wp_lo, st))
         return rc;
+    // fp16 head/tail operands of the same weights: re-split lazily at their next use (ensure_h16).  Opt-in
+    // (LVSR_F16_GEMM=1): the GEMM class drops from 1.89 to 1.63 ms at the metric batch, but the extra device allocations move
+    // the workspace to other physical pages, and the persistent decoder happened to lose more than that on the benchmarked
+    // allocation sequence (51.2 -> 55.3 us per step; placement sweep in profiles/r2k_summary.md).
+    m->use_h16 = getenv("LVSR_F16_GEMM") != nullptr && atoi(getenv("LVSR_F16_GEMM")) != 0;
+    m->h16_stale = true;
   }
   // fork(feedback(y)) for every symbol y, once: [(V+1), 3C]
   if (c.one_of_n_feedback) {
@@ -528,7 +587,21 @@ int lvsr_encoder_forward(lvsr_model* m, const float* x, const float* mask, int32
     const int rows = Tl * B;
     float* pre = m->ws.f32((size_t)rows * 6 * D);
     LVSR_CHECK(pre, "out of device memory (encoder pre-activations)");
-    if (m->use_tc && l < (int)m->Wcat_hi.size() && m->Wcat_hi[l] && gemm_tc_supported(rows, 6 * D, din)) {
+    static const int h16_mask_e = getenv("LVSR_F16_GEMM_MASK") ? atoi(getenv("LVSR_F16_GEMM_MASK")) : 3;
+    if (l == 1 && (h16_mask_e & 1))
+      if (int rc = ensure_h16(m, st)) return rc;
+    if ((h16_mask_e & 1) && m->use_tc && m->use_h16 && l < (int)m->Wcat_h16_head.size() && m->Wcat_h16_head[l] && gemm_tc_h16_supported(rows, 6 * D, din)) {
+      // input = the previous layer's BiGRU output: fp16 head/tail operands (gemm_tc.cu)
+      const size_t mark = m->ws.off;
+      const size_t halfs = (size_t)rows * gemm_tc_kpad_h16(din);
+      float* a_h = m->ws.f32((halfs + 1) / 2);
+      float* a_t = m->ws.f32((halfs + 1) / 2);
+      LVSR_CHECK(a_h && a_t, "out of device memory (fp16 split scratch)");
+      if (int rc = gemm_tc_h16(cur, a_h, a_t, rows, din, m->Wcat_h16_head[l], m->Wcat_h16_tail[l], m->Wcat_h16_scale[l], 6 * D,
+                               m->bcat[l], pre, 6 * D, st))
+        return rc;
+      if (m->ws.off <= m->ws.cap) m->ws.off = mark;
+    } else if (m->use_tc && l < (int)m->Wcat_hi.size() && m->Wcat_hi[l] && gemm_tc_supported(rows, 6 * D, din)) {
       const size_t mark = m->ws.off;
       float* a_hi = m->ws.f32((size_t)rows * gemm_tc_kpad(din));
       float* a_lo = m->ws.f32((size_t)rows * gemm_tc_kpad(din));
@@ -564,6 +637,18 @@ int lvsr_preprocess(lvsr_model* m, const float* attended, int32_t Tp, int32_t U,
   if (int rc = check_ready(m)) return rc;
   LVSR_CHECK(attended && out && Tp > 0 && U > 0, "preprocess: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int h16_mask_p = getenv("LVSR_F16_GEMM_MASK") ? atoi(getenv("LVSR_F16_GEMM_MASK")) : 3;
+  if (h16_mask_p & 2)
+    if (int rc = ensure_h16(m, st)) return rc;
+  if ((h16_mask_p & 2) && m->use_tc && m->use_h16 && m->Wp_h16_head && gemm_tc_h16_supported(Tp * U, m->cfg.dim_matcher, m->E)) {
+    ArenaScope scope(m, st);
+    const size_t halfs = (size_t)Tp * U * gemm_tc_kpad_h16(m->E);
+    float* a_h = m->ws.f32((halfs + 1) / 2);
+    float* a_t = m->ws.f32((halfs + 1) / 2);
+    LVSR_CHECK(a_h && a_t, "out of device memory (fp16 split scratch)");
+    return gemm_tc_h16(attended, a_h, a_t, Tp * U, m->E, m->Wp_h16_head, m->Wp_h16_tail, m->Wp_h16_scale, m->cfg.dim_matcher,
+                       m->P(std::string(ATT) + "/preprocess.b"), out, m->cfg.dim_matcher, st);
+  }
   if (m->use_tc && m->Wp_hi && gemm_tc_supported(Tp * U, m->cfg.dim_matcher, m->E)) {
     ArenaScope scope(m, st);
     float* a_hi = m->ws.f32((size_t)Tp * U * gemm_tc_kpad(m->E));

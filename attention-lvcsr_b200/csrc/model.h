@@ -49,12 +49,14 @@ struct Arena {
   void reserve(size_t bytes, cudaStream_t stream) {
     if (off != 0 || bytes <= cap) return;
     if (cudaStreamSynchronize(stream) != cudaSuccess) return;
-    if (base) cudaFree(base);
+    if (base) cudaFree(base - shift);
     base = nullptr;
     cap = 0;
-    if (cudaMalloc(reinterpret_cast<void**>(&base), bytes) == cudaSuccess) cap = bytes;
+    shift = getenv("LVSR_WS_SHIFT_KB") ? (size_t)atoll(getenv("LVSR_WS_SHIFT_KB")) * 1024 : 0;   // placement experiments
+    if (cudaMalloc(reinterpret_cast<void**>(&base), bytes + shift) == cudaSuccess) { cap = bytes; base += shift; }
     else cudaGetLastError();
   }
+  size_t shift = 0;
   void enter() { depth++; }
   // returns non-zero on CUDA failure
   int leave(cudaStream_t stream) {
@@ -66,12 +68,12 @@ struct Arena {
       if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
       for (void* p : overflow) cudaFree(p);
       overflow.clear();
-      if (base) cudaFree(base);
+      if (base) cudaFree(base - shift);
       base = nullptr;
       const size_t want = (size_t)((used + overflow_bytes) * 1.25) + (1 << 20);
       overflow_bytes = 0;
       cap = 0;
-      if (cudaMalloc(reinterpret_cast<void**>(&base), want) == cudaSuccess) cap = want;
+      if (cudaMalloc(reinterpret_cast<void**>(&base), want + shift) == cudaSuccess) { cap = want; base += shift; }
       else cudaGetLastError();
     }
     return 0;
@@ -79,7 +81,7 @@ struct Arena {
   void destroy() {
     for (void* p : overflow) cudaFree(p);
     overflow.clear();
-    if (base) cudaFree(base);
+    if (base) cudaFree(base - shift);
     base = nullptr;
     cap = off = 0;
   }
@@ -119,6 +121,14 @@ struct lvsr_model {
   std::vector<float*> Wcat_hi, Wcat_lo;
   float *Wp_hi = nullptr, *Wp_lo = nullptr;
   bool use_tc = true;
+  // fp16 head/tail splits of the same weights for the inference projections whose input is a BiGRU output (layers >= 1,
+  // preprocess): K-major [N, Kpad64] halfs + {scale, 1/scale} on the device; null = tf32 path
+  std::vector<void*> Wcat_h16_head, Wcat_h16_tail;
+  std::vector<float*> Wcat_h16_scale;
+  void *Wp_h16_head = nullptr, *Wp_h16_tail = nullptr;
+  float* Wp_h16_scale = nullptr;
+  bool use_h16 = true;
+  bool h16_stale = true;            // the fp16 operands do not match the parameters (re-split at the next use)
   float v_bias = 0.f;               // host copy of energy_comp/linear.b
   unsigned* status = nullptr;       // device word: launch status of the data-flow decoder (common.cuh LVSR_FLOW_*)
   bool force_stepwise = false;      // set while a failed persistent launch is re-run on the step-wise kernels
