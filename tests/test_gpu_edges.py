@@ -260,4 +260,4 @@ def test_fp16_split_projection_gemm_opt_in(monkeypatch):
     d_att = float((att - ref_att).abs().max() / ref_att.abs().max())
     d_cost = float((rec.cost_matrix(labels, lm, att, attm, return_all=True)["costs"] - ref_pre).abs().max() / ref_pre.abs().max())
     print("fp16-split GEMM vs oracle", errs, "vs 3xTF32", d_att, d_cost)
-    assert d_att < 1e-5 and d_cost < 1e-5
+    assert d_att < 2e-5 and d_cost < TOL, (d_att, d_cost)
